@@ -1,0 +1,150 @@
+/*
+ * viprs_b200 -- C ABI of the B200-native coordinate-ascent E-step.
+ *
+ * This is the drop-in boundary for the reference's Cython layer
+ * /root/reference/viprs/model/vi/e_step_cpp.pyx (cpp_e_step :91-122, cpp_e_step_mixture :125-159,
+ * cpp_e_step_grid :161-195, check_omp_support/check_blas_support :71-76), i.e. what a ctypes / cffi
+ * binding on the reference side would load instead of the compiled `e_step_cpp` module.
+ * Plain pointers and sizes only; no torch / numpy types.  Every function returns 0 on success,
+ * a negative VIPRS_B200_E* code for argument errors, or a positive cudaError_t.  Nothing throws.
+ *
+ * Conventions
+ *   T  : floating type of the variational state (f32 | f64)         -- `floating` in e_step_cpp.pxd
+ *   U  : LD storage type (i8 | i16 | f32 | f64)                     -- `noncomplex_numeric` (.pxd:11-17)
+ *   I  : CSR index type (int32 | int64)                             -- `indptr_type` (.pxd:7-9)
+ *   LD : magenpy's "CSR without column indices": row j stores the contiguous column run
+ *        [left_bound[j], left_bound[j] + indptr[j+1]-indptr[j])      (e_step.hpp:389-392).
+ *        Both the upper-triangular (`low_memory=True`, diagonal excluded) and the symmetric layout
+ *        (`low_memory=False`, run includes the unit diagonal) are accepted; only the strictly
+ *        upper part (column > row) is kept on the device.
+ *   "dev" pointers are CUDA device pointers; "host" pointers are ordinary host memory.
+ *   `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef VIPRS_B200_H
+#define VIPRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- dtype / memory-kind enums ------------------------------------------------------------ */
+#define VIPRS_B200_I8   0
+#define VIPRS_B200_I16  1
+#define VIPRS_B200_F32  2
+#define VIPRS_B200_F64  3
+
+#define VIPRS_B200_MEM_HOST   0
+#define VIPRS_B200_MEM_DEVICE 1
+
+/* ---- error codes (negative; positive values are cudaError_t) ------------------------------ */
+#define VIPRS_B200_OK               0
+#define VIPRS_B200_EINVAL          -1   /* bad argument (null pointer, bad dtype, M <= 0 ...)        */
+#define VIPRS_B200_ELAYOUT         -2   /* LD arrays inconsistent (run leaves [0,M), negative length) */
+#define VIPRS_B200_EBLOCK_TOO_LARGE -3  /* an LD block (connected run of overlapping rows) does not
+                                           fit the per-CTA shared-memory state; non-block (windowed /
+                                           banded genome-wide) LD lands here                          */
+#define VIPRS_B200_ENOMEM          -4
+#define VIPRS_B200_ENODEVICE       -5   /* no CUDA device: there is NO CPU fallback                  */
+#define VIPRS_B200_EUNSUPPORTED    -6   /* (T,U) combination or K not built                          */
+
+/* ---- library / device queries ------------------------------------------------------------- */
+const char* viprs_b200_version(void);
+const char* viprs_b200_strerror(int code);
+/* replaces check_omp_support / check_blas_support (e_step_cpp.pyx:71-76): number of visible CUDA
+ * devices (0 => every compute entry point returns VIPRS_B200_ENODEVICE). */
+int viprs_b200_device_count(void);
+
+/* ---- device-resident LD matrix ------------------------------------------------------------ */
+typedef struct viprs_b200_ld viprs_b200_ld_t;
+
+typedef struct {
+    int32_t M;               /* rows (SNPs)                                                   */
+    int32_t ld_dtype;        /* VIPRS_B200_I8 ...                                             */
+    int32_t n_blocks;        /* independent LD blocks found                                   */
+    int32_t max_block;       /* rows in the largest block                                     */
+    int32_t n_panels;        /* row panels (units of the TMA ring)                            */
+    int32_t stage_bytes;     /* shared-memory ring stage size the panels were cut for         */
+    int64_t nnz;             /* strictly-upper stored entries (algorithmic LD elements)       */
+    int64_t packed_elems;    /* elements in the 16B-aligned device layout (nnz + padding)     */
+    int64_t smem_bytes;      /* dynamic shared memory per CTA the sweep kernel will request   */
+} viprs_b200_ld_info_t;
+
+/* Replaces the reference's LD load (VIPRS.py:153-172: ld_mat.load(...) -> ld_data/ld_indptr/
+ * leftmost_idx kept in host RAM).  Copies (if mem_kind == HOST) and re-lays the matrix into the
+ * 16-byte-aligned row layout described in DESIGN.md, finds the independent LD blocks and cuts the
+ * row panels.  indptr_is_i64: 1 for int64 indptr, 0 for int32.  stage_bytes = 0 picks the default. */
+int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int32_t* left_bound,
+                         const void* indptr, int32_t indptr_is_i64, const void* ld_data,
+                         int32_t ld_dtype, int32_t mem_kind, int32_t stage_bytes, void* stream);
+int viprs_b200_ld_info(const viprs_b200_ld_t* ld, viprs_b200_ld_info_t* info);
+/* first row of every LD block, n_blocks+1 entries (host pointer out) */
+int viprs_b200_ld_block_rows(const viprs_b200_ld_t* ld, int32_t* out_host);
+int viprs_b200_ld_destroy(viprs_b200_ld_t* ld);
+
+/* ---- E-step sweeps on a device-resident LD matrix (all array arguments are DEVICE pointers) --
+ *
+ * viprs_b200_e_step_{f32,f64}: one Gauss-Seidel sweep with the semantics of
+ * e_step<T,U,I>(..., threads=1, low_memory=true) (e_step.hpp:343-442), same argument meaning and
+ * order as cpp_e_step (e_step_cpp.pyx:91-105).  `threads` / `low_memory` have no equivalent: the
+ * sweep is always the strictly sequential order and the LD is always upper-triangular on device.
+ *
+ * q handling: the sweep reads the LD once.  It leaves in `q` the forward part
+ * dq_scale * sum_{i<j} R_ij eta_i(new).  If materialize_q != 0 a second streaming pass adds the
+ * backward part so that `q` equals the reference's q after its second pass
+ * (update_q_factor, e_step.hpp:307-338).  On entry `q` is ignored: the backward part is recomputed
+ * from `eta`, which must therefore be consistent with (var_gamma, var_mu) as it is in the reference
+ * (VIPRS.py:355-358).
+ *
+ * sums (optional, may be NULL): device double[VIPRS_B200_NSUMS] receiving the per-sweep reductions
+ * the M-step / ELBO need (see VIPRS_B200_S_* below).
+ */
+#define VIPRS_B200_NSUMS 12
+#define VIPRS_B200_S_GAMMA        0  /* sum gamma_j                         (VIPRS.py:434)          */
+#define VIPRS_B200_S_GAMMA_MU2    1  /* sum gamma_j mu_j^2                  (zeta, VIPRS.py:896)    */
+#define VIPRS_B200_S_ETA_QF       2  /* sum eta_j * qF_j ; eta'(R-I)eta = 2x (VIPRS.py:455)          */
+#define VIPRS_B200_S_BETA_ETA     3  /* sum std_beta_j eta_j                (VIPRS.py:469)          */
+#define VIPRS_B200_S_G_LOGG       4  /* sum g log g, g clipped [1e-15,1-1e-15] (VIPRS.py:512,562)   */
+#define VIPRS_B200_S_NG_LOGNG     5  /* sum (1-g) log(1-g), clipped         (VIPRS.py:516,563)      */
+#define VIPRS_B200_S_ETA2         6  /* sum eta_j^2                         (VIPRS.py:703)          */
+#define VIPRS_B200_S_MAX_DIFF     7  /* max |eta_diff_j|                    (VIPRS.py:997)          */
+#define VIPRS_B200_S_G_INV_TAU    8  /* sum gamma_j / var_tau_j   (needs n_per_snp; else 0)         */
+#define VIPRS_B200_S_G_LOG_TAU    9  /* sum gamma_j log var_tau_j (needs n_per_snp; else 0)         */
+#define VIPRS_B200_S_GCLIP        10 /* sum of clipped gamma_j              (VIPRS.py:565)          */
+#define VIPRS_B200_S_RESERVED     11
+
+int viprs_b200_e_step_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
+                          float* var_mu, float* eta, float* q, float* eta_diff,
+                          const float* u_logs, const float* sqrt_half_var_tau, const float* mu_mult,
+                          float dq_scale, int32_t materialize_q, void* stream);
+int viprs_b200_e_step_f64(const viprs_b200_ld_t* ld, const double* std_beta, double* var_gamma,
+                          double* var_mu, double* eta, double* q, double* eta_diff,
+                          const double* u_logs, const double* sqrt_half_var_tau,
+                          const double* mu_mult, double dq_scale, int32_t materialize_q,
+                          void* stream);
+
+/* q[j] += dq_scale * sum_{k>j} R_jk x[k]  -- the reference's update_q_factor (e_step.hpp:307-338)
+ * as a stand-alone streaming kernel (x = eta for materialisation, or any vector). */
+int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float* q,
+                                float dq_scale, void* stream);
+int viprs_b200_backward_dot_f64(const viprs_b200_ld_t* ld, const double* x, double* q,
+                                double dq_scale, void* stream);
+
+/* ---- one-shot host-pointer drop-ins: exactly the reference's cpdef signatures -----------------
+ * Same arrays, same in-place outputs as cpp_e_step(...) (e_step_cpp.pyx:91-122) with host (numpy)
+ * buffers: upload, pack, sweep, materialise q, download.  `threads` is accepted and ignored
+ * (the result is the threads=1 result); `low_memory` selects how the LD run is interpreted
+ * (1: upper-triangular, 0: symmetric with diagonal).  On entry q must be consistent with eta
+ * as in the reference; it is recomputed on the device. */
+int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, const void* ld_indptr,
+                          int32_t indptr_is_i64, const void* ld_data, int32_t ld_dtype,
+                          int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu,
+                          void* eta, void* q, void* eta_diff, const void* u_logs,
+                          const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
+                          int32_t threads, int32_t low_memory);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPRS_B200_H */

@@ -1,0 +1,261 @@
+// viprs_b200 -- device-resident LD matrix: host-side planning (LD blocks, row panels) and the
+// re-layout kernel that turns magenpy's CSR-without-column-indices (consumer: e_step.hpp:389-392,
+// producer call site: VIPRS.py:167-172) into the 16-byte-aligned row layout the sweep streams
+// with 1-D TMA bulk copies.  See DESIGN.md "Data layout in HBM".
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "ld.h"
+
+namespace vb {
+
+template <typename U>
+__global__ void pack_rows_kernel(int M, const U* __restrict__ src, const int64_t* __restrict__ src_off,
+                                 const int32_t* __restrict__ cs, const int32_t* __restrict__ ce,
+                                 const int64_t* __restrict__ prow, const int32_t* __restrict__ pcs,
+                                 U* __restrict__ dst) {
+    // one warp per row; 8 rows per CTA
+    const int row = blockIdx.x * (blockDim.x / WARP) + (threadIdx.x / WARP);
+    if (row >= M) return;
+    const int lane = threadIdx.x % WARP;
+    const int64_t p0 = prow[row];
+    const int plen = (int)(prow[row + 1] - p0);
+    const int c0 = pcs[row], a = cs[row], b = ce[row];
+    const int64_t so = src_off[row];
+    for (int e = lane; e < plen; e += WARP) {
+        const int col = c0 + e;
+        U v = U(0);
+        if (col >= a && col < b) v = src[so + (col - a)];
+        dst[p0 + e] = v;
+    }
+}
+
+static int elem_size(int dt) {
+    switch (dt) {
+        case VIPRS_B200_I8: return 1;
+        case VIPRS_B200_I16: return 2;
+        case VIPRS_B200_F32: return 4;
+        case VIPRS_B200_F64: return 8;
+    }
+    return 0;
+}
+
+}  // namespace vb
+
+#define CUDA_TRY(x)                          \
+    do {                                     \
+        cudaError_t _e = (x);                \
+        if (_e != cudaSuccess) {             \
+            rc = (int)_e;                    \
+            goto fail;                       \
+        }                                    \
+    } while (0)
+
+extern "C" int viprs_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char* viprs_b200_version(void) { return "viprs_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char* viprs_b200_strerror(int code) {
+    switch (code) {
+        case VIPRS_B200_OK: return "ok";
+        case VIPRS_B200_EINVAL: return "invalid argument";
+        case VIPRS_B200_ELAYOUT: return "inconsistent LD layout (row run leaves [0, M) or negative length)";
+        case VIPRS_B200_EBLOCK_TOO_LARGE:
+            return "an LD block does not fit the per-CTA shared-memory state (non-block / banded LD is not supported)";
+        case VIPRS_B200_ENOMEM: return "out of memory";
+        case VIPRS_B200_ENODEVICE: return "no CUDA device (there is no CPU fallback)";
+        case VIPRS_B200_EUNSUPPORTED: return "unsupported dtype combination";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int32_t* left_bound,
+                                    const void* indptr, int32_t indptr_is_i64, const void* ld_data,
+                                    int32_t ld_dtype, int32_t mem_kind, int32_t stage_bytes, void* stream_) {
+    if (!out || M <= 0 || !left_bound || !indptr) return VIPRS_B200_EINVAL;
+    const int esize = vb::elem_size(ld_dtype);
+    if (esize == 0) return VIPRS_B200_EINVAL;
+    if (viprs_b200_device_count() <= 0) return VIPRS_B200_ENODEVICE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int epv = 16 / esize;
+    if (stage_bytes <= 0) stage_bytes = vb::kDefaultStageBytes;
+    stage_bytes &= ~15;
+
+    int rc = VIPRS_B200_OK;
+    viprs_b200_ld* h = new (std::nothrow) viprs_b200_ld();
+    if (!h) return VIPRS_B200_ENOMEM;
+    void* d_raw = nullptr;        // staging copy of the caller's ld_data when it lives on the host
+    int64_t* d_src_off = nullptr;
+    int32_t *d_cs = nullptr, *d_ce = nullptr;
+
+    // ---- host copies of the index arrays -------------------------------------------------
+    std::vector<int32_t> lb(M);
+    std::vector<int64_t> ip((size_t)M + 1);
+    {
+        const size_t ipb = (size_t)(M + 1) * (indptr_is_i64 ? 8 : 4);
+        std::vector<unsigned char> tmp(ipb);
+        if (mem_kind == VIPRS_B200_MEM_DEVICE) {
+            CUDA_TRY(cudaMemcpyAsync(lb.data(), left_bound, (size_t)M * 4, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(tmp.data(), indptr, ipb, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        } else {
+            std::memcpy(lb.data(), left_bound, (size_t)M * 4);
+            std::memcpy(tmp.data(), indptr, ipb);
+        }
+        if (indptr_is_i64) {
+            std::memcpy(ip.data(), tmp.data(), ipb);
+        } else {
+            const int32_t* p32 = reinterpret_cast<const int32_t*>(tmp.data());
+            for (int j = 0; j <= M; ++j) ip[j] = p32[j];
+        }
+    }
+    {
+        // ---- per-row runs (strictly upper part), LD blocks ----------------------------------
+        std::vector<int32_t> cs(M), ce(M), pcs(M);
+        std::vector<int64_t> src_off(M), prow((size_t)M + 1);
+        std::vector<int32_t> blk_row;
+        int64_t nnz = 0;
+        int32_t runmax = 0;
+        for (int j = 0; j < M; ++j) {
+            const int64_t len = ip[j + 1] - ip[j];
+            if (len < 0 || lb[j] < 0 || (int64_t)lb[j] + len > M) { rc = VIPRS_B200_ELAYOUT; goto fail; }
+            int64_t a = lb[j], b = (int64_t)lb[j] + len;
+            int64_t skip = std::max<int64_t>(0, (int64_t)j + 1 - a);   // symmetric layout: drop columns <= j
+            if (skip > len) skip = len;
+            a += skip;
+            if (a >= b) { a = b = j + 1; }
+            cs[j] = (int32_t)a; ce[j] = (int32_t)b; src_off[j] = ip[j] + skip;
+            nnz += b - a;
+            if (j == 0 || runmax <= j) blk_row.push_back(j);   // no earlier row reaches column j
+            runmax = std::max<int32_t>(runmax, (int32_t)b);
+        }
+        blk_row.push_back(M);
+        const int nb = (int)blk_row.size() - 1;
+
+        // ---- aligned packed rows, panels ----------------------------------------------------
+        std::vector<int32_t> blk_panel(nb + 1), panel_row;
+        std::vector<int64_t> blk_cost(nb);
+        int64_t off = 0;
+        int32_t max_block = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = blk_row[b], r1 = blk_row[b + 1];
+            max_block = std::max(max_block, r1 - r0);
+            blk_panel[b] = (int32_t)panel_row.size();
+            int64_t pbytes = 0; int prows = 0; int64_t cost = 0;
+            for (int j = r0; j < r1; ++j) {
+                int32_t a = r0 + ((cs[j] - r0) / epv) * epv;
+                int32_t e = r0 + ((ce[j] - r0 + epv - 1) / epv) * epv;
+                if (ce[j] == cs[j]) { e = a; }
+                pcs[j] = a; prow[j] = off;
+                const int64_t rb = (int64_t)(e - a) * esize;
+                if (rb > stage_bytes) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
+                if (prows == 0 || prows == vb::PMAX || pbytes + rb > stage_bytes) {
+                    panel_row.push_back(j); prows = 0; pbytes = 0;
+                }
+                ++prows; pbytes += rb; off += (e - a); cost += (e - a) + 64;
+            }
+            blk_cost[b] = cost;
+        }
+        prow[M] = off;
+        blk_panel[nb] = (int32_t)panel_row.size();
+        const int np = (int)panel_row.size();
+        panel_row.push_back(M);
+
+        std::vector<int32_t> order(nb);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return blk_cost[a] > blk_cost[b]; });
+
+        h->M = M; h->ld_dtype = ld_dtype; h->esize = esize; h->epv = epv; h->nnz = nnz;
+        h->packed_elems = off; h->n_blocks = nb; h->max_block = max_block; h->n_panels = np;
+        h->stage_bytes = stage_bytes; h->h_blk_row = blk_row;
+        CUDA_TRY(cudaGetDevice(&h->device));
+
+        // ---- device arrays ------------------------------------------------------------------
+        CUDA_TRY(cudaMalloc(&h->d_packed, (size_t)std::max<int64_t>(off, 16) * esize + 64));
+        CUDA_TRY(cudaMalloc(&h->d_prow, sizeof(int64_t) * ((size_t)M + 1)));
+        CUDA_TRY(cudaMalloc(&h->d_pcs, sizeof(int32_t) * (size_t)M));
+        CUDA_TRY(cudaMalloc(&h->d_blk_row, sizeof(int32_t) * (nb + 1)));
+        CUDA_TRY(cudaMalloc(&h->d_blk_panel, sizeof(int32_t) * (nb + 1)));
+        CUDA_TRY(cudaMalloc(&h->d_panel_row, sizeof(int32_t) * (np + 1)));
+        CUDA_TRY(cudaMalloc(&h->d_blk_order, sizeof(int32_t) * nb));
+        CUDA_TRY(cudaMalloc(&d_src_off, sizeof(int64_t) * (size_t)M));
+        CUDA_TRY(cudaMalloc(&d_cs, sizeof(int32_t) * (size_t)M));
+        CUDA_TRY(cudaMalloc(&d_ce, sizeof(int32_t) * (size_t)M));
+        CUDA_TRY(cudaMemcpyAsync(h->d_prow, prow.data(), sizeof(int64_t) * ((size_t)M + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_pcs, pcs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_blk_row, blk_row.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_blk_panel, blk_panel.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_panel_row, panel_row.data(), sizeof(int32_t) * (np + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_blk_order, order.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(int64_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_cs, cs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_ce, ce.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+
+        const void* d_src = ld_data;
+        const int64_t total_in = ip[M];
+        if (mem_kind != VIPRS_B200_MEM_DEVICE) {
+            CUDA_TRY(cudaMalloc(&d_raw, (size_t)std::max<int64_t>(total_in, 1) * esize));
+            if (total_in > 0) {
+                if (!ld_data) { rc = VIPRS_B200_EINVAL; goto fail; }
+                CUDA_TRY(cudaMemcpyAsync(d_raw, ld_data, (size_t)total_in * esize, cudaMemcpyHostToDevice, stream));
+            }
+            d_src = d_raw;
+        }
+        {
+            const int wpb = 8;
+            dim3 grid((M + wpb - 1) / wpb), block(wpb * vb::WARP);
+            switch (ld_dtype) {
+                case VIPRS_B200_I8:
+                    vb::pack_rows_kernel<int8_t><<<grid, block, 0, stream>>>(M, (const int8_t*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (int8_t*)h->d_packed);
+                    break;
+                case VIPRS_B200_I16:
+                    vb::pack_rows_kernel<int16_t><<<grid, block, 0, stream>>>(M, (const int16_t*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (int16_t*)h->d_packed);
+                    break;
+                case VIPRS_B200_F32:
+                    vb::pack_rows_kernel<float><<<grid, block, 0, stream>>>(M, (const float*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (float*)h->d_packed);
+                    break;
+                default:
+                    vb::pack_rows_kernel<double><<<grid, block, 0, stream>>>(M, (const double*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (double*)h->d_packed);
+                    break;
+            }
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaStreamSynchronize(stream));   // host vectors above are about to go out of scope
+    }
+    cudaFree(d_raw); cudaFree(d_src_off); cudaFree(d_cs); cudaFree(d_ce);
+    *out = h;
+    return VIPRS_B200_OK;
+
+fail:
+    cudaGetLastError();
+    cudaFree(d_raw); cudaFree(d_src_off); cudaFree(d_cs); cudaFree(d_ce);
+    viprs_b200_ld_destroy(h);
+    return rc;
+}
+
+extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
+    if (!h) return VIPRS_B200_OK;
+    cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
+    cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_blk_order);
+    delete h;
+    return VIPRS_B200_OK;
+}
+
+extern "C" int viprs_b200_ld_block_rows(const viprs_b200_ld_t* h, int32_t* out_host) {
+    if (!h || !out_host) return VIPRS_B200_EINVAL;
+    std::memcpy(out_host, h->h_blk_row.data(), sizeof(int32_t) * h->h_blk_row.size());
+    return VIPRS_B200_OK;
+}

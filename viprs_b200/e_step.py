@@ -1,0 +1,84 @@
+"""
+Drop-in replacements for the reference's Cython entry points
+(/root/reference/viprs/model/vi/e_step_cpp.pyx): same names, same positional arguments, same
+in-place outputs.  numpy arguments take the one-shot host path of the C ABI
+(upload + sweep + download inside the call); torch CUDA tensors take the device path and re-use a
+cached device-resident LD matrix.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ld import DeviceLD, _NP_DT, _stream_ptr
+
+_FLOAT_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+_ld_cache = {}
+
+
+def check_omp_support():
+    """e_step_cpp.pyx:75-76 -- there is no OpenMP path here; kept for API compatibility."""
+    return False
+
+
+def check_blas_support():
+    """e_step_cpp.pyx:71-72 -- there is no BLAS path here; kept for API compatibility."""
+    return False
+
+
+def device_ld_for(ld_left_bound, ld_indptr, ld_data):
+    """Device LD cache for callers that pass the same CUDA tensors every iteration."""
+    key = (ld_data.data_ptr(), ld_data.numel(), ld_data.dtype, ld_indptr.data_ptr(), ld_left_bound.data_ptr())
+    ld = _ld_cache.get(key)
+    if ld is None:
+        if len(_ld_cache) > 64:
+            _ld_cache.clear()
+        ld = DeviceLD(ld_data, ld_indptr, ld_left_bound)
+        _ld_cache[key] = ld
+    return ld
+
+
+def e_step_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult,
+                  dq_scale, materialize_q=True):
+    """One sweep on a DeviceLD; all arrays are contiguous torch CUDA tensors of one float dtype."""
+    L = _lib.lib()
+    ts = (std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult)
+    dt = var_mu.dtype
+    for t in ts:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and t.numel() == ld.M):
+            raise ValueError("e_step_device: arrays must be contiguous CUDA tensors of length M and one dtype")
+    fn = L.viprs_b200_e_step_f32 if dt == torch.float32 else L.viprs_b200_e_step_f64
+    rc = fn(ld.handle, *[t.data_ptr() for t in ts], float(dq_scale), int(bool(materialize_q)), _stream_ptr())
+    _lib.check(rc, "viprs_b200_e_step")
+
+
+def cpp_e_step(ld_left_bound, ld_indptr, ld_data, std_beta, var_gamma, var_mu, eta, q, eta_diff,
+               u_logs, sqrt_half_var_tau, mu_mult, dq_scale, threads=1, low_memory=True):
+    """
+    cpp_e_step (e_step_cpp.pyx:91-122).  ``threads`` is accepted and ignored: the result is always the
+    strictly sequential (threads=1) sweep.  ``q`` on entry must be consistent with ``eta`` (as it always
+    is in VIPRS.fit); on exit it equals the reference's q after update_q_factor.
+    """
+    if isinstance(ld_data, torch.Tensor):
+        ld = device_ld_for(ld_left_bound, ld_indptr, ld_data)
+        return e_step_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau,
+                             mu_mult, dq_scale, True)
+    L = _lib.lib()
+    M = var_mu.shape[0]
+    fdt = _FLOAT_DT[var_mu.dtype]
+    lb = np.ascontiguousarray(ld_left_bound, dtype=np.int32)
+    ip = np.ascontiguousarray(ld_indptr)
+    if ip.dtype not in (np.int32, np.int64):
+        ip = ip.astype(np.int64)
+    ins = [np.ascontiguousarray(a, dtype=var_mu.dtype) for a in (std_beta, u_logs, sqrt_half_var_tau, mu_mult)]
+    for a in (var_gamma, var_mu, eta, q, eta_diff):
+        if not (a.flags["C_CONTIGUOUS"] and a.dtype == var_mu.dtype and a.shape[0] == M):
+            raise ValueError("cpp_e_step: in/out arrays must be C-contiguous, length M, one float dtype")
+    ld_data = np.ascontiguousarray(ld_data)
+    rc = L.viprs_b200_cpp_e_step(M, lb.ctypes.data, ip.ctypes.data, int(ip.dtype == np.int64),
+                                 ld_data.ctypes.data, _NP_DT[ld_data.dtype], fdt, ins[0].ctypes.data,
+                                 var_gamma.ctypes.data, var_mu.ctypes.data, eta.ctypes.data, q.ctypes.data,
+                                 eta_diff.ctypes.data, ins[1].ctypes.data, ins[2].ctypes.data, ins[3].ctypes.data,
+                                 float(dq_scale), int(threads), int(bool(low_memory)))
+    _lib.check(rc, "viprs_b200_cpp_e_step")
