@@ -426,7 +426,6 @@ class OracleVIPRSMix(OracleVIPRS):
         # value cached at initialisation (VIPRS.py:359).
         log_var_tau = _dict_concat(self._log_var_tau)
         pi, null_pi, tau_beta = self.pi, self.get_null_pi(), self.tau_beta
-        zeta_mk = {c: (v * (self.var_mu[c] ** 2 + (1.0 / self.var_tau[c]))) for c, v in self.var_gamma.items()}
         elbo = 0.
         elbo -= np.log(2 * np.pi * self.sigma_epsilon)
         if "sigma_epsilon" not in self.fix_params:
@@ -439,5 +438,8 @@ class OracleVIPRSMix(OracleVIPRS):
         elbo -= np.multiply(var_gamma, np.log(var_gamma) - np.log(pi)).sum(axis=sum_axis)
         elbo -= np.multiply(null_gamma, np.log(null_gamma) - np.log(null_pi)).sum(axis=sum_axis)
         elbo += .5 * np.multiply(var_gamma, 1. - log_var_tau + np.log(tau_beta)).sum(axis=sum_axis)
-        elbo -= .5 * (tau_beta * _dict_concat(zeta_mk).astype(np.float64)).sum(axis=sum_axis)
+        # zeta is (M,) and tau_beta is a (K,) array here => the `else` branch of VIPRS.py:568-573
+        var_mu = _dict_concat(self.var_mu)
+        var_tau = _dict_concat(self.var_tau)
+        elbo -= .5 * (np.multiply(var_gamma, tau_beta) * (var_mu ** 2 + 1. / var_tau)).sum(axis=sum_axis)
         return elbo

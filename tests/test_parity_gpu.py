@@ -1,0 +1,154 @@
+"""
+GPU parity tests: the CUDA path, called through the C ABI, against the oracle (compiled reference when
+present, else the C port) on the same seeded inputs.  Tolerances are BASELINE.json's: 1e-4 relative
+(float32 state), 1e-10 (float64 state), max-norm relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relmax
+from tests_util import make_block_ld
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-4, np.float64: 1e-10}
+LD_DT = {"i8": np.int8, "i16": np.int16, "f32": np.float32, "f64": np.float64}
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import viprs_b200
+    return viprs_b200
+
+
+def _hyper(rng, P, T, pi=0.02, se=0.8):
+    M = P["M"]
+    n = np.floor(rng.uniform(4e4, 6e4, M))
+    tau = pi * M / (1 - se)
+    vt = n / se + tau
+    u_logs = (np.log(pi) - np.log(1 - pi) + .5 * (np.log(tau) - np.log(vt))).astype(T)
+    return u_logs, np.sqrt(.5 * vt).astype(T), (n / (vt * se)).astype(T), pi
+
+
+def _sweeps(fn, P, T, hy, n_sweeps, low_memory=True, **kw):
+    M = P["M"]
+    u_logs, shvt, mm, pi = hy
+    st = {k: np.zeros(M, T) for k in ("var_mu", "eta", "q", "eta_diff")}
+    st["var_gamma"] = np.full(M, pi, T)
+    for _ in range(n_sweeps):
+        fn(P["lb"], P["indptr"], P["data"], P["beta"], st["var_gamma"], st["var_mu"], st["eta"], st["q"],
+           st["eta_diff"], u_logs, shvt, mm, P["dq"], 1, low_memory, **kw)
+    return st
+
+
+@pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f32", "i16"), ("f32", "f32"), ("f64", "f64"), ("f64", "i8"),
+                                   ("f64", "f32"), ("f64", "i16")])
+@pytest.mark.parametrize("n_sweeps", [1, 2, 10])
+def test_cpp_e_step_host_dropin_matches_oracle(vb, oracle_built, tn, un, n_sweeps):
+    T = np.float32 if tn == "f32" else np.float64
+    rng = np.random.default_rng(100 + n_sweeps)
+    P = make_block_ld(rng, (257, 64, 1, 2, 33, 700, 17), LD_DT[un], T)
+    hy = _hyper(rng, P, T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, n_sweeps)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, n_sweeps)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= TOL[T], (k, relmax(got[k], ref[k]))
+
+
+@pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f64", "f64")])
+def test_symmetric_layout_matches_oracle(vb, oracle_built, tn, un):
+    """`low_memory=False` (symmetric rows incl. the unit diagonal, e_step.hpp:423-428)."""
+    T = np.float32 if tn == "f32" else np.float64
+    rng = np.random.default_rng(7)
+    Ps = make_block_ld(rng, (120, 45, 300), LD_DT[un], T, symmetric=True)
+    hy = _hyper(rng, Ps, T)
+    ref = _sweeps(oracle_built.e_step, Ps, T, hy, 3, low_memory=False)
+    got = _sweeps(vb.cpp_e_step, Ps, T, hy, 3, low_memory=False)
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        assert relmax(got[k], ref[k]) <= TOL[T], (k, relmax(got[k], ref[k]))
+
+
+def test_large_block_and_ragged_rows(vb, oracle_built):
+    """One 4096-SNP block (the BASELINE block size) + windowed rows that stop before the block end."""
+    T = np.float32
+    rng = np.random.default_rng(3)
+    P = make_block_ld(rng, (4096, 500), np.int8, T)
+    hy = _hyper(rng, P, T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 2)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 2)
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        assert relmax(got[k], ref[k]) <= 1e-4, (k, relmax(got[k], ref[k]))
+    # ragged: truncate every row's run to at most 100 columns (banded inside the block)
+    lens = np.diff(P["indptr"])
+    keep = np.minimum(lens, 100)
+    idx = np.concatenate([np.arange(s, s + k) for s, k in zip(P["indptr"][:-1], keep)])
+    Q = dict(P)
+    Q["data"] = P["data"][idx]
+    Q["indptr"] = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+    ref = _sweeps(oracle_built.e_step, Q, T, hy, 3)
+    got = _sweeps(vb.cpp_e_step, Q, T, hy, 3)
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        assert relmax(got[k], ref[k]) <= 1e-4, (k, relmax(got[k], ref[k]))
+
+
+def test_golden_raw_sweeps(vb):
+    """Against the committed reference outputs (no oracle involved): cpp_e_step f64 / int16 LD."""
+    d, ch = load_golden("cpp_e_step_f64_i16.npz")
+    c = ch[0]
+    M = len(c["std_beta"])
+    st = {k: np.zeros(M) for k in ("var_mu", "eta", "q", "eta_diff")}
+    st["var_gamma"] = np.full(M, 0.03)
+    for sweep in (1, 2):
+        vb.cpp_e_step(c["ld_left_bound"], c["ld_indptr"], c["ld_data"], c["std_beta"], st["var_gamma"], st["var_mu"],
+                      st["eta"], st["q"], st["eta_diff"], d["raw_u_logs"], d["raw_sqrt_half_var_tau"],
+                      d["raw_mu_mult"], 1. / 32767, 1, True)
+        for k, a in st.items():
+            assert relmax(a, d[f"raw_sweep{sweep}_{k}"]) <= 1e-10, (sweep, k)
+
+
+def test_device_path_and_ld_info(vb, oracle_built):
+    import torch
+    T = np.float32
+    rng = np.random.default_rng(5)
+    P = make_block_ld(rng, (300, 200, 100), np.int16, T)
+    hy = _hyper(rng, P, T)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    assert ld.M == P["M"] and ld.n_blocks == 3 and ld.max_block == 300
+    assert ld.nnz == P["indptr"][-1]
+    assert list(ld.block_rows()) == [0, 300, 500, 600]
+    u_logs, shvt, mm, pi = hy
+    M = P["M"]
+    dev = {k: torch.zeros(M, dtype=torch.float32, device="cuda") for k in ("var_mu", "eta", "q", "eta_diff")}
+    dev["var_gamma"] = torch.full((M,), pi, dtype=torch.float32, device="cuda")
+    c = lambda a: torch.from_numpy(a).cuda()
+    beta, ul, sv, mmd = c(P["beta"]), c(u_logs), c(shvt), c(mm)
+    for _ in range(4):
+        vb.e_step_device(ld, beta, dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"], ul, sv, mmd,
+                         P["dq"], True)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 4)
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        assert relmax(dev[k].cpu().numpy(), ref[k]) <= 1e-4, k
+    # q == dq * (R - I) eta  (size-independent property)
+    q2 = torch.zeros(M, dtype=torch.float32, device="cuda")
+    ld.backward_dot(dev["eta"], q2, P["dq"])
+    R = np.zeros((M, M))
+    for j in range(M):
+        s, e = P["indptr"][j], P["indptr"][j + 1]
+        R[j, P["lb"][j]:P["lb"][j] + (e - s)] = P["data"][s:e]
+    eta = dev["eta"].cpu().numpy().astype(np.float64)
+    assert relmax(q2.cpu().numpy(), P["dq"] * (R @ eta)) <= 1e-5
+    assert relmax(dev["q"].cpu().numpy(), P["dq"] * ((R + R.T) @ eta)) <= 1e-4
+
+
+def test_non_block_ld_is_refused(vb):
+    """A single huge 'block' (banded genome-wide LD) must be refused, not silently mis-computed."""
+    M = 120000
+    lb = np.arange(1, M + 1, dtype=np.int32)
+    lens = np.minimum(8, M - 1 - np.arange(M)).astype(np.int64)
+    ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    data = np.zeros(int(ip[-1]), np.int8)
+    with pytest.raises(vb.ViprsB200Error) as ei:
+        vb.DeviceLD(data, ip, lb)
+    assert ei.value.code == -3
