@@ -68,7 +68,9 @@ typedef struct {
     int32_t stage_bytes;     /* shared-memory ring stage size the panels were cut for         */
     int64_t nnz;             /* strictly-upper stored entries (algorithmic LD elements)       */
     int64_t packed_elems;    /* elements in the 16B-aligned device layout (nnz + padding)     */
-    int64_t smem_bytes;      /* dynamic shared memory per CTA the sweep kernel will request   */
+    int64_t smem_bytes;      /* dynamic shared memory per CTA the float32 sweep will request  */
+    int32_t ring_stages;     /* depth of the TMA ring (float32 state)                         */
+    int32_t ctas_per_sm;     /* CTAs (LD blocks) that share one SM (float32 state)            */
 } viprs_b200_ld_info_t;
 
 /* Replaces the reference's LD load (VIPRS.py:153-172: ld_mat.load(...) -> ld_data/ld_indptr/
@@ -124,6 +126,19 @@ int viprs_b200_e_step_f64(const viprs_b200_ld_t* ld, const double* std_beta, dou
                           const double* mu_mult, double dq_scale, int32_t materialize_q,
                           void* stream);
 
+/* viprs_b200_e_step_mixture_{f32,f64}: one sweep with the semantics of e_step_mixture<T,U,I>(..., threads=1,
+ * low_memory=true) (e_step.hpp:447-551); argument meaning and order of cpp_e_step_mixture
+ * (e_step_cpp.pyx:125-141).  var_gamma, var_mu, u_logs, sqrt_half_var_tau, mu_mult are (M,K) C-order;
+ * eta, q, eta_diff, std_beta, log_null_pi have M entries.  1 <= K <= 16. */
+int viprs_b200_e_step_mixture_f32(const viprs_b200_ld_t* ld, int32_t K, const float* std_beta, float* var_gamma,
+                                  float* var_mu, float* eta, float* q, float* eta_diff, const float* log_null_pi,
+                                  const float* u_logs, const float* sqrt_half_var_tau, const float* mu_mult,
+                                  float dq_scale, int32_t materialize_q, void* stream);
+int viprs_b200_e_step_mixture_f64(const viprs_b200_ld_t* ld, int32_t K, const double* std_beta, double* var_gamma,
+                                  double* var_mu, double* eta, double* q, double* eta_diff,
+                                  const double* log_null_pi, const double* u_logs, const double* sqrt_half_var_tau,
+                                  const double* mu_mult, double dq_scale, int32_t materialize_q, void* stream);
+
 /* q[j] += dq_scale * sum_{k>j} R_jk x[k]  -- the reference's update_q_factor (e_step.hpp:307-338)
  * as a stand-alone streaming kernel (x = eta for materialisation, or any vector). */
 int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float* q,
@@ -143,6 +158,14 @@ int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, const void* l
                           void* eta, void* q, void* eta_diff, const void* u_logs,
                           const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
                           int32_t threads, int32_t low_memory);
+
+/* cpp_e_step_mixture(...) (e_step_cpp.pyx:125-159) with host buffers; K = var_mu.shape[1]. */
+int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_bound, const void* ld_indptr,
+                                  int32_t indptr_is_i64, const void* ld_data, int32_t ld_dtype,
+                                  int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu,
+                                  void* eta, void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
+                                  const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
+                                  int32_t threads, int32_t low_memory);
 
 #ifdef __cplusplus
 }

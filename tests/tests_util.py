@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def make_block_ld(rng, blocks, ld_dtype, T, symmetric=False, k=16, alpha=0.5, n=5e4):
+def make_block_ld(rng, blocks, ld_dtype, T, symmetric=False, k=16, alpha=0.5, n=5e4, effect=0.006, p_causal=0.02):
     """Block-diagonal PD LD in magenpy's CSR-without-column-indices layout (upper-triangular, or the
     symmetric `low_memory=False` layout with the unit diagonal)."""
     ld_dtype = np.dtype(ld_dtype)
@@ -14,7 +14,7 @@ def make_block_ld(rng, blocks, ld_dtype, T, symmetric=False, k=16, alpha=0.5, n=
         dinv = 1. / np.sqrt(np.diag(C))
         R = alpha * C * dinv[:, None] * dinv[None, :]
         np.fill_diagonal(R, 1.)
-        betas.append(R @ (rng.standard_normal(B) * 0.02 * (rng.random(B) < 0.1)) + rng.standard_normal(B) / np.sqrt(n))
+        betas.append(R @ (rng.standard_normal(B) * effect * (rng.random(B) < p_causal)) + rng.standard_normal(B) / np.sqrt(n))
         if ld_dtype == np.int8:
             Rq = np.rint(R * 127.).astype(np.int8)
         elif ld_dtype == np.int16:

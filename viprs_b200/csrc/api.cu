@@ -1,136 +1,88 @@
-// viprs_b200 -- C ABI entry points (include/viprs_b200.h) for the sweep kernels.
+// viprs_b200 -- C ABI entry points (include/viprs_b200.h): LD info and the one-shot host-pointer drop-ins.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <vector>
 
 #include "common.cuh"
 #include "ld.h"
-#include "sweep.cuh"
-
-namespace vb {
-
-constexpr int kNBW = 8;   // bulk warps per CTA (CTA = 320 threads)
-
-size_t sweep_smem_bytes(int max_block, int epv, int tsize, int stage_bytes, int nbw) {
-    (void)epv;
-    return make_layout(state_pad(max_block), tsize, stage_bytes, nbw).total;
-}
-
-static int max_optin_smem(int device) {
-    int v = 0;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    return v;
-}
-
-template <typename T, typename U>
-static int launch_sweep(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
-                        T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq, cudaStream_t st) {
-    SweepParams<T> p;
-    p.packed = ld->d_packed; p.prow = ld->d_prow; p.pcs = ld->d_pcs; p.blk_row = ld->d_blk_row;
-    p.blk_panel = ld->d_blk_panel; p.panel_row = ld->d_panel_row; p.blk_order = ld->d_blk_order;
-    p.n_blocks = ld->n_blocks; p.stage_bytes = ld->stage_bytes; p.bpad = state_pad(ld->max_block);
-    p.std_beta = std_beta; p.var_gamma = var_gamma; p.var_mu = var_mu; p.eta = eta; p.q = q;
-    p.eta_diff = eta_diff; p.u_logs = u_logs; p.sqrt_half_var_tau = shvt; p.mu_mult = mu_mult; p.dq_scale = dq;
-    const size_t smem = make_layout(p.bpad, (int)sizeof(T), p.stage_bytes, kNBW).total;
-    if ((int64_t)smem > (int64_t)max_optin_smem(ld->device)) return VIPRS_B200_EBLOCK_TOO_LARGE;
-    auto kern = sweep_kernel<T, U, kNBW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<ld->n_blocks, (kNBW + 2) * WARP, smem, st>>>(p);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
-}
-
-template <typename T, typename U>
-static int launch_backward(const viprs_b200_ld* ld, const T* x, T* q, T dq, cudaStream_t st) {
-    const int wpb = 8;
-    backward_dot_kernel<T, U><<<(ld->M + wpb - 1) / wpb, wpb * WARP, 0, st>>>(
-        ld->M, (const U*)ld->d_packed, ld->d_prow, ld->d_pcs, x, q, dq);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
-}
-
-template <typename T>
-static int e_step_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
-                           T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq,
-                           int materialize_q, cudaStream_t st) {
-    if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
-        return VIPRS_B200_EINVAL;
-    int rc;
-    switch (ld->ld_dtype) {
-        case VIPRS_B200_I8:
-            rc = launch_sweep<T, int8_t>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq, st);
-            if (rc == 0 && materialize_q) rc = launch_backward<T, int8_t>(ld, eta, q, dq, st);
-            return rc;
-        case VIPRS_B200_I16:
-            rc = launch_sweep<T, int16_t>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq, st);
-            if (rc == 0 && materialize_q) rc = launch_backward<T, int16_t>(ld, eta, q, dq, st);
-            return rc;
-        case VIPRS_B200_F32:
-            rc = launch_sweep<T, float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq, st);
-            if (rc == 0 && materialize_q) rc = launch_backward<T, float>(ld, eta, q, dq, st);
-            return rc;
-        case VIPRS_B200_F64:
-            if (sizeof(T) == 4) return VIPRS_B200_EUNSUPPORTED;
-            if constexpr (sizeof(T) == 8) {
-                rc = launch_sweep<T, double>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq, st);
-                if (rc == 0 && materialize_q) rc = launch_backward<T, double>(ld, eta, q, dq, st);
-                return rc;
-            }
-    }
-    return VIPRS_B200_EUNSUPPORTED;
-}
-
-template <typename T>
-static int backward_dispatch(const viprs_b200_ld* ld, const T* x, T* q, T dq, cudaStream_t st) {
-    if (!ld || !x || !q) return VIPRS_B200_EINVAL;
-    switch (ld->ld_dtype) {
-        case VIPRS_B200_I8: return launch_backward<T, int8_t>(ld, x, q, dq, st);
-        case VIPRS_B200_I16: return launch_backward<T, int16_t>(ld, x, q, dq, st);
-        case VIPRS_B200_F32: return launch_backward<T, float>(ld, x, q, dq, st);
-        case VIPRS_B200_F64:
-            if constexpr (sizeof(T) == 8) return launch_backward<T, double>(ld, x, q, dq, st);
-    }
-    return VIPRS_B200_EUNSUPPORTED;
-}
-
-}  // namespace vb
 
 extern "C" int viprs_b200_ld_info(const viprs_b200_ld_t* h, viprs_b200_ld_info_t* info) {
     if (!h || !info) return VIPRS_B200_EINVAL;
     info->M = h->M; info->ld_dtype = h->ld_dtype; info->n_blocks = h->n_blocks; info->max_block = h->max_block;
     info->n_panels = h->n_panels; info->stage_bytes = h->stage_bytes; info->nnz = h->nnz;
     info->packed_elems = h->packed_elems;
-    info->smem_bytes = (int64_t)vb::sweep_smem_bytes(h->max_block, h->epv, 4, h->stage_bytes, vb::kNBW);
+    const vb::RingGeometry g = vb::ring_geometry(h, 4);
+    info->smem_bytes = g.smem_bytes;
+    info->ring_stages = g.nst;
+    info->ctas_per_sm = g.ctas_per_sm;
     return VIPRS_B200_OK;
 }
 
-extern "C" int viprs_b200_e_step_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
-                                     float* var_mu, float* eta, float* q, float* eta_diff, const float* u_logs,
-                                     const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
-                                     int32_t materialize_q, void* stream) {
-    return vb::e_step_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs,
-                                      sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, (cudaStream_t)stream);
+// ---- one-shot host-pointer drop-ins ------------------------------------------------------------------
+namespace {
+
+struct DevBuf {            // n arrays of nb bytes each, uploaded from host pointers
+    unsigned char* d = nullptr;
+    ~DevBuf() { cudaFree(d); }
+};
+
+// K == 0: cpp_e_step; K > 0: cpp_e_step_mixture
+int host_dropin(int32_t M, int32_t K, const int32_t* lb, const void* indptr, int32_t is64, const void* ld_data,
+                int32_t ld_dtype, int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu, void* eta,
+                void* q, void* eta_diff, const void* log_null_pi, const void* u_logs, const void* shvt,
+                const void* mu_mult, double dq_scale) {
+    if (float_dtype != VIPRS_B200_F32 && float_dtype != VIPRS_B200_F64) return VIPRS_B200_EINVAL;
+    if (!std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
+        return VIPRS_B200_EINVAL;
+    if (K > 0 && !log_null_pi) return VIPRS_B200_EINVAL;
+    viprs_b200_ld_t* ld = nullptr;
+    int rc = viprs_b200_ld_create(&ld, M, lb, indptr, is64, ld_data, ld_dtype, VIPRS_B200_MEM_HOST, 0, nullptr);
+    if (rc) return rc;
+    const size_t ts = float_dtype == VIPRS_B200_F32 ? 4 : 8;
+    const size_t kk = K > 0 ? (size_t)K : 1;
+    const size_t n1 = (size_t)M * ts, nk = n1 * kk;
+    // layout: [beta n1][eta n1][q n1][diff n1][lnp n1][gamma nk][mu nk][ulogs nk][shvt nk][mm nk]
+    DevBuf buf;
+    cudaError_t e = cudaMalloc(&buf.d, 5 * n1 + 5 * nk);
+    if (e != cudaSuccess) { viprs_b200_ld_destroy(ld); return (int)e; }
+    unsigned char* d = buf.d;
+    unsigned char *d_beta = d, *d_eta = d + n1, *d_q = d + 2 * n1, *d_diff = d + 3 * n1, *d_lnp = d + 4 * n1;
+    unsigned char *d_g = d + 5 * n1, *d_mu = d_g + nk, *d_ul = d_mu + nk, *d_sv = d_ul + nk, *d_mm = d_sv + nk;
+    auto up = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, 0);
+    };
+    up(d_beta, std_beta, n1); up(d_eta, eta, n1); up(d_q, q, n1); up(d_diff, eta_diff, n1);
+    if (K > 0) up(d_lnp, log_null_pi, n1);
+    up(d_g, var_gamma, nk); up(d_mu, var_mu, nk); up(d_ul, u_logs, nk); up(d_sv, shvt, nk); up(d_mm, mu_mult, nk);
+    if (e == cudaSuccess) {
+        if (ts == 4) {
+            using F = float;
+            rc = K > 0 ? viprs_b200_e_step_mixture_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
+                                                       (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr)
+                       : viprs_b200_e_step_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
+                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr);
+        } else {
+            using F = double;
+            rc = K > 0 ? viprs_b200_e_step_mixture_f64(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
+                                                       (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr)
+                       : viprs_b200_e_step_f64(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
+                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr);
+        }
+    }
+    auto down = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, 0);
+    };
+    down(var_gamma, d_g, nk); down(var_mu, d_mu, nk); down(eta, d_eta, n1); down(q, d_q, n1); down(eta_diff, d_diff, n1);
+    cudaError_t e2 = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = e2;
+    viprs_b200_ld_destroy(ld);
+    if (rc) return rc;
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
 }
 
-extern "C" int viprs_b200_e_step_f64(const viprs_b200_ld_t* ld, const double* std_beta, double* var_gamma,
-                                     double* var_mu, double* eta, double* q, double* eta_diff,
-                                     const double* u_logs, const double* sqrt_half_var_tau,
-                                     const double* mu_mult, double dq_scale, int32_t materialize_q, void* stream) {
-    return vb::e_step_dispatch<double>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs,
-                                       sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, (cudaStream_t)stream);
-}
+}  // namespace
 
-extern "C" int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float* q, float dq_scale,
-                                           void* stream) {
-    return vb::backward_dispatch<float>(ld, x, q, dq_scale, (cudaStream_t)stream);
-}
-extern "C" int viprs_b200_backward_dot_f64(const viprs_b200_ld_t* ld, const double* x, double* q,
-                                           double dq_scale, void* stream) {
-    return vb::backward_dispatch<double>(ld, x, q, dq_scale, (cudaStream_t)stream);
-}
-
-// One-shot host-pointer drop-in for cpp_e_step (e_step_cpp.pyx:91-122).
+// cpp_e_step (e_step_cpp.pyx:91-122)
 extern "C" int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, const void* ld_indptr,
                                      int32_t indptr_is_i64, const void* ld_data, int32_t ld_dtype,
                                      int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu,
@@ -138,37 +90,19 @@ extern "C" int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, co
                                      const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
                                      int32_t threads, int32_t low_memory) {
     (void)threads; (void)low_memory;   // always the threads=1 order; the layout is detected per row
-    if (float_dtype != VIPRS_B200_F32 && float_dtype != VIPRS_B200_F64) return VIPRS_B200_EINVAL;
-    if (!std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !sqrt_half_var_tau || !mu_mult)
-        return VIPRS_B200_EINVAL;
-    viprs_b200_ld_t* ld = nullptr;
-    int rc = viprs_b200_ld_create(&ld, M, ld_left_bound, ld_indptr, indptr_is_i64, ld_data, ld_dtype,
-                                  VIPRS_B200_MEM_HOST, 0, nullptr);
-    if (rc) return rc;
-    const size_t ts = float_dtype == VIPRS_B200_F32 ? 4 : 8;
-    const size_t nb = (size_t)M * ts;
-    unsigned char* d = nullptr;   // 9 arrays: beta, gamma, mu, eta, q, diff, ulogs, shvt, mm
-    cudaError_t e = cudaMalloc(&d, 9 * nb);
-    if (e != cudaSuccess) { viprs_b200_ld_destroy(ld); return (int)e; }
-    const void* hin[9] = {std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult};
-    for (int i = 0; i < 9 && e == cudaSuccess; ++i)
-        e = cudaMemcpyAsync(d + i * nb, hin[i], nb, cudaMemcpyHostToDevice, 0);
-    if (e == cudaSuccess) {
-        if (ts == 4)
-            rc = viprs_b200_e_step_f32(ld, (float*)(d), (float*)(d + nb), (float*)(d + 2 * nb), (float*)(d + 3 * nb),
-                                       (float*)(d + 4 * nb), (float*)(d + 5 * nb), (float*)(d + 6 * nb),
-                                       (float*)(d + 7 * nb), (float*)(d + 8 * nb), (float)dq_scale, 1, nullptr);
-        else
-            rc = viprs_b200_e_step_f64(ld, (double*)(d), (double*)(d + nb), (double*)(d + 2 * nb), (double*)(d + 3 * nb),
-                                       (double*)(d + 4 * nb), (double*)(d + 5 * nb), (double*)(d + 6 * nb),
-                                       (double*)(d + 7 * nb), (double*)(d + 8 * nb), dq_scale, 1, nullptr);
-    }
-    void* hout[5] = {var_gamma, var_mu, eta, q, eta_diff};
-    for (int i = 0; i < 5 && e == cudaSuccess && rc == 0; ++i)
-        e = cudaMemcpyAsync(hout[i], d + (i + 1) * nb, nb, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    cudaFree(d);
-    viprs_b200_ld_destroy(ld);
-    if (rc) return rc;
-    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+    return host_dropin(M, 0, ld_left_bound, ld_indptr, indptr_is_i64, ld_data, ld_dtype, float_dtype, std_beta,
+                       var_gamma, var_mu, eta, q, eta_diff, nullptr, u_logs, sqrt_half_var_tau, mu_mult, dq_scale);
+}
+
+// cpp_e_step_mixture (e_step_cpp.pyx:125-159)
+extern "C" int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_bound, const void* ld_indptr,
+                                             int32_t indptr_is_i64, const void* ld_data, int32_t ld_dtype,
+                                             int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu,
+                                             void* eta, void* q, void* eta_diff, const void* log_null_pi,
+                                             const void* u_logs, const void* sqrt_half_var_tau, const void* mu_mult,
+                                             double dq_scale, int32_t threads, int32_t low_memory) {
+    (void)threads; (void)low_memory;
+    if (K < 1) return VIPRS_B200_EINVAL;
+    return host_dropin(M, K, ld_left_bound, ld_indptr, indptr_is_i64, ld_data, ld_dtype, float_dtype, std_beta,
+                       var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs, sqrt_half_var_tau, mu_mult, dq_scale);
 }

@@ -1,5 +1,6 @@
-// viprs_b200 -- shared device helpers (sm_100a): mbarrier / 1-D TMA bulk copy PTX wrappers,
-// LD element decoding (int8/int16 dequantised in registers), small warp utilities.
+// viprs_b200 -- shared device helpers (sm_100a): mbarrier / 1-D TMA bulk copy PTX wrappers, shared-memory
+// release/acquire counters, LD element decoding (int8/int16 dequantised in registers, packed f32x2 math),
+// small warp utilities.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,9 +9,14 @@
 namespace vb {
 
 constexpr int WARP = 32;
-constexpr int PMAX = 16;        // rows per panel (chain-warp window is 2*PMAX = 32 lanes)
-constexpr int NSTAGE = 4;       // TMA ring depth (panels u-2 (axpy), u-1 (chain), u (dot), u+1 (in flight))
-constexpr int NSLOT = 4;        // ring depth of the small per-panel mailboxes (dot partials, eta_new)
+constexpr int PMAX = 16;        // max rows per panel (one TMA bulk copy)
+constexpr int BATCH = 16;       // rows the chain warp retires between two hand-shakes
+constexpr int RR = 128;         // per-row ring slots (row metadata, dot partials, eta_new); needs NST <= 8
+constexpr int NST_MAX = 8;      // max TMA ring depth
+constexpr int NBW = 8;          // bulk warps per CTA
+constexpr int NBT = NBW * WARP;
+constexpr int WIN = 33;         // row j's forward axpy is done by the chain warp for columns < cut_j,
+                                // cut_j = ceil((j + WIN) / EPV) * EPV  (block-local), by the bulk warps from cut_j on
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk-copy wrappers
@@ -42,8 +48,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Every spin-wait in the sweep is bounded: a protocol bug traps (cudaErrorLaunchFailure) instead of hanging the GPU.
+constexpr uint32_t kSpinLimit = 1u << 27;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
     }
 }
 // 1-D TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
@@ -55,11 +65,58 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// 1-D TMA prefetch into L2 only (fire and forget): deep prefetch without spending shared memory.
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// monotonic shared-memory counters with release / acquire semantics (CTA scope)
+__device__ __forceinline__ void red_release_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t target) {
+    uint32_t spins = 0;
+    while (ld_acquire(p) < target) {
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 math (sm_100: FFMA2 / FADD2 -- two IEEE fp32 operations per issue slot)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%6,%7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
 
 // ---------------------------------------------------------------------------------------------
 // LD element traits.  One "vector" is 16 bytes of LD data = EPV elements.
-// decode() turns the 16 bytes into EPV values of the state type T (exact for integer codes:
-// the dequantisation scale is folded into scalars, as in e_step.hpp:421 `dq_scale*eta_diff_j`).
+// Integer codes are stored BIASED on the device (int8: code ^ 0x80, int16: code ^ 0x8000; zero padding is
+// 0x80 / 0x8000), so that a byte permute straight into the mantissa of 2^23 followed by one exact
+// subtraction yields the code as fp32 -- no I2F, no sign fix-up.  The dequantisation scale is folded into
+// scalars as in the reference (e_step.hpp:421 `dq_scale * eta_diff_j`).
 // ---------------------------------------------------------------------------------------------
 template <typename U> struct LdTraits;
 template <> struct LdTraits<int8_t>  { static constexpr int EPV = 16; static constexpr int DT = VIPRS_B200_I8; };
@@ -67,75 +124,153 @@ template <> struct LdTraits<int16_t> { static constexpr int EPV = 8;  static con
 template <> struct LdTraits<float>   { static constexpr int EPV = 4;  static constexpr int DT = VIPRS_B200_F32; };
 template <> struct LdTraits<double>  { static constexpr int EPV = 2;  static constexpr int DT = VIPRS_B200_F64; };
 
-// int8 -> fp32 without I2F: place the (sign-flipped) byte in the low mantissa bits of 2^23 and
-// subtract 2^23+128.  One PRMT + one FADD per element, both exact.
-__device__ __forceinline__ void decode4_i8(uint32_t w, float* o) {
-    const uint32_t x = w ^ 0x80808080u;
-    o[0] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540)) - 8388736.0f;
-    o[1] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7541)) - 8388736.0f;
-    o[2] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7542)) - 8388736.0f;
-    o[3] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7543)) - 8388736.0f;
-}
-__device__ __forceinline__ void decode2_i16(uint32_t w, float* o) {
-    const uint32_t x = w ^ 0x80008000u;
-    o[0] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7410)) - 8421376.0f;
-    o[1] = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7432)) - 8421376.0f;
-}
+constexpr float kMagicI8 = 8388736.0f;    // 2^23 + 128
+constexpr float kMagicI16 = 8421376.0f;   // 2^23 + 32768
 
-template <typename T, typename U> struct Decode;
+// accumulator type of a 16-byte-vector dot product
+template <typename T> struct Pk;
+template <> struct Pk<float> {
+    using acc_t = float2;
+    static __device__ __forceinline__ acc_t zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float sum(acc_t a) { return a.x + a.y; }
+};
+template <> struct Pk<double> {
+    using acc_t = double;
+    static __device__ __forceinline__ acc_t zero() { return 0.0; }
+    static __device__ __forceinline__ double sum(acc_t a) { return a; }
+};
 
-template <> struct Decode<float, int8_t> {
-    static __device__ __forceinline__ void vec(const uint4& v, float* o) {
-        decode4_i8(v.x, o); decode4_i8(v.y, o + 4); decode4_i8(v.z, o + 8); decode4_i8(v.w, o + 12);
+// VecOps<T,U>: dot(c, x, acc): acc += sum_e code_e * x[e];  axpy(c, a, f): f[e] += code_e * a
+template <typename T, typename U> struct VecOps;
+
+template <> struct VecOps<float, int8_t> {
+    static __device__ __forceinline__ void pairs(uint32_t w, float2& p0, float2& p1) {
+        p0 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                         __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)));
+        p1 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
+                         __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)));
+        const float2 m = make_float2(-kMagicI8, -kMagicI8);
+        p0 = add2(p0, m);
+        p1 = add2(p1, m);
+    }
+    static __device__ __forceinline__ void dot(const uint4& c, const float* x, float2& acc) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 p0, p1;
+            pairs(w[i], p0, p1);
+            acc = fma2(p0, make_float2(x[4 * i], x[4 * i + 1]), acc);
+            acc = fma2(p1, make_float2(x[4 * i + 2], x[4 * i + 3]), acc);
+        }
+    }
+    static __device__ __forceinline__ void axpy(const uint4& c, float a, float* f) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+        const float2 aa = make_float2(a, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 p0, p1;
+            pairs(w[i], p0, p1);
+            const float2 r0 = fma2(p0, aa, make_float2(f[4 * i], f[4 * i + 1]));
+            const float2 r1 = fma2(p1, aa, make_float2(f[4 * i + 2], f[4 * i + 3]));
+            f[4 * i] = r0.x; f[4 * i + 1] = r0.y; f[4 * i + 2] = r1.x; f[4 * i + 3] = r1.y;
+        }
     }
 };
-template <> struct Decode<float, int16_t> {
-    static __device__ __forceinline__ void vec(const uint4& v, float* o) {
-        decode2_i16(v.x, o); decode2_i16(v.y, o + 2); decode2_i16(v.z, o + 4); decode2_i16(v.w, o + 6);
+template <> struct VecOps<float, int16_t> {
+    static __device__ __forceinline__ float2 pair(uint32_t w) {
+        float2 p = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)),
+                               __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)));
+        return add2(p, make_float2(-kMagicI16, -kMagicI16));
+    }
+    static __device__ __forceinline__ void dot(const uint4& c, const float* x, float2& acc) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = fma2(pair(w[i]), make_float2(x[2 * i], x[2 * i + 1]), acc);
+    }
+    static __device__ __forceinline__ void axpy(const uint4& c, float a, float* f) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+        const float2 aa = make_float2(a, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 r = fma2(pair(w[i]), aa, make_float2(f[2 * i], f[2 * i + 1]));
+            f[2 * i] = r.x; f[2 * i + 1] = r.y;
+        }
     }
 };
-template <> struct Decode<float, float> {
-    static __device__ __forceinline__ void vec(const uint4& v, float* o) {
-        o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y); o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
+template <> struct VecOps<float, float> {
+    static __device__ __forceinline__ void dot(const uint4& c, const float* x, float2& acc) {
+        acc = fma2(make_float2(__uint_as_float(c.x), __uint_as_float(c.y)), make_float2(x[0], x[1]), acc);
+        acc = fma2(make_float2(__uint_as_float(c.z), __uint_as_float(c.w)), make_float2(x[2], x[3]), acc);
+    }
+    static __device__ __forceinline__ void axpy(const uint4& c, float a, float* f) {
+        const float2 aa = make_float2(a, a);
+        const float2 r0 = fma2(make_float2(__uint_as_float(c.x), __uint_as_float(c.y)), aa, make_float2(f[0], f[1]));
+        const float2 r1 = fma2(make_float2(__uint_as_float(c.z), __uint_as_float(c.w)), aa, make_float2(f[2], f[3]));
+        f[0] = r0.x; f[1] = r0.y; f[2] = r1.x; f[3] = r1.y;
     }
 };
-template <> struct Decode<double, int8_t> {
+// double state: plain scalar decode + DFMA (these configurations are HBM-bound by a wide margin)
+template <typename U> struct DecodeD;
+template <> struct DecodeD<int8_t> {
     static __device__ __forceinline__ void vec(const uint4& v, double* o) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) o[4 * i + b] = (double)(int)(int8_t)(w[i] >> (8 * b));
+            for (int b = 0; b < 4; ++b) o[4 * i + b] = (double)((int)((w[i] >> (8 * b)) & 0xffu) - 128);
     }
 };
-template <> struct Decode<double, int16_t> {
+template <> struct DecodeD<int16_t> {
     static __device__ __forceinline__ void vec(const uint4& v, double* o) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            o[2 * i] = (double)(int)(int16_t)(w[i] & 0xffffu);
-            o[2 * i + 1] = (double)(int)(int16_t)(w[i] >> 16);
+            o[2 * i] = (double)((int)(w[i] & 0xffffu) - 32768);
+            o[2 * i + 1] = (double)((int)(w[i] >> 16) - 32768);
         }
     }
 };
-template <> struct Decode<double, float> {
+template <> struct DecodeD<float> {
     static __device__ __forceinline__ void vec(const uint4& v, double* o) {
         o[0] = (double)__uint_as_float(v.x); o[1] = (double)__uint_as_float(v.y);
         o[2] = (double)__uint_as_float(v.z); o[3] = (double)__uint_as_float(v.w);
     }
 };
-template <> struct Decode<double, double> {
+template <> struct DecodeD<double> {
     static __device__ __forceinline__ void vec(const uint4& v, double* o) {
         o[0] = __hiloint2double((int)v.y, (int)v.x);
         o[1] = __hiloint2double((int)v.w, (int)v.z);
     }
 };
+template <typename U> struct VecOps<double, U> {
+    static constexpr int EPV = LdTraits<U>::EPV;
+    static __device__ __forceinline__ void dot(const uint4& c, const double* x, double& acc) {
+        double v[EPV];
+        DecodeD<U>::vec(c, v);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc = fma(v[e], x[e], acc);
+    }
+    static __device__ __forceinline__ void axpy(const uint4& c, double a, double* f) {
+        double v[EPV];
+        DecodeD<U>::vec(c, v);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) f[e] = fma(v[e], a, f[e]);
+    }
+};
 
-// scalar element fetch from shared memory (chain warp's window coefficients)
-template <typename T, typename U>
-__device__ __forceinline__ T ld_elem(const unsigned char* base, int byte_off) {
-    return static_cast<T>(*reinterpret_cast<const U*>(base + byte_off));
+// scalar element fetch from the device layout (biased integer codes) -> value in the state type
+template <typename T, typename U> __device__ __forceinline__ T ld_elem(const unsigned char* p);
+template <> __device__ __forceinline__ float ld_elem<float, int8_t>(const unsigned char* p) { return (float)((int)*p - 128); }
+template <> __device__ __forceinline__ float ld_elem<float, int16_t>(const unsigned char* p) {
+    return (float)((int)*reinterpret_cast<const uint16_t*>(p) - 32768);
 }
+template <> __device__ __forceinline__ float ld_elem<float, float>(const unsigned char* p) { return *reinterpret_cast<const float*>(p); }
+template <> __device__ __forceinline__ double ld_elem<double, int8_t>(const unsigned char* p) { return (double)((int)*p - 128); }
+template <> __device__ __forceinline__ double ld_elem<double, int16_t>(const unsigned char* p) {
+    return (double)((int)*reinterpret_cast<const uint16_t*>(p) - 32768);
+}
+template <> __device__ __forceinline__ double ld_elem<double, float>(const unsigned char* p) { return (double)*reinterpret_cast<const float*>(p); }
+template <> __device__ __forceinline__ double ld_elem<double, double>(const unsigned char* p) { return *reinterpret_cast<const double*>(p); }
 
 // fused multiply-add in the state type: std::fma in the reference (e_step.hpp:101,173)
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
@@ -144,15 +279,16 @@ __device__ __forceinline__ float exp_t(float x) { return expf(x); }
 __device__ __forceinline__ double exp_t(double x) { return exp(x); }
 __device__ __forceinline__ float abs_t(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
+__device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 
-// two-branch stable sigmoid, e_step.hpp:245-261
+// stable sigmoid, e_step.hpp:245-261 (two-branch form evaluated branch-free: e = exp(-|x|),
+// x >= 0: 1/(1+e);  x < 0: e/(1+e))
 template <typename T>
 __device__ __forceinline__ T sigmoid_t(T x) {
-    if (x < T(0)) {
-        const T ex = exp_t(x);
-        return ex / (T(1) + ex);
-    }
-    return T(1) / (T(1) + exp_t(-x));
+    const T e = exp_t(-abs_t(x));
+    const T r = rcp_t(T(1) + e);
+    return x < T(0) ? e * r : r;
 }
 
 template <typename T>
@@ -167,6 +303,33 @@ __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v += shfl_xor_t(v, m);
     return v;
+}
+
+// Reduce 8 per-lane accumulators across the warp with 9 shuffles: on return acc[0] of lane l holds the
+// warp total of accumulator  r = 4*bit4(l) + 2*bit3(l) + bit2(l).
+template <typename T>
+__device__ __forceinline__ int warp_reduce8(T* acc, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T send = b4 ? acc[i] : acc[i + 4];
+        const T keep = b4 ? acc[i + 4] : acc[i];
+        acc[i] = keep + shfl_xor_t(send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = b3 ? acc[i] : acc[i + 2];
+        const T keep = b3 ? acc[i + 2] : acc[i];
+        acc[i] = keep + shfl_xor_t(send, 8);
+    }
+    {
+        const T send = b2 ? acc[0] : acc[1];
+        const T keep = b2 ? acc[1] : acc[0];
+        acc[0] = keep + shfl_xor_t(send, 4);
+    }
+    acc[0] += shfl_xor_t(acc[0], 2);
+    acc[0] += shfl_xor_t(acc[0], 1);
+    return (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
 }
 
 }  // namespace vb

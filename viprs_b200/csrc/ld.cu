@@ -9,10 +9,19 @@
 #include <numeric>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ld.h"
+#include "sweep.cuh"
 
 namespace vb {
+
+// integer codes are stored biased (see common.cuh): int8 ^ 0x80, int16 ^ 0x8000
+__device__ __forceinline__ int8_t bias(int8_t v) { return (int8_t)(v ^ (int8_t)0x80); }
+__device__ __forceinline__ int16_t bias(int16_t v) { return (int16_t)(v ^ (int16_t)0x8000); }
+__device__ __forceinline__ float bias(float v) { return v; }
+__device__ __forceinline__ double bias(double v) { return v; }
 
 template <typename U>
 __global__ void pack_rows_kernel(int M, const U* __restrict__ src, const int64_t* __restrict__ src_off,
@@ -31,7 +40,7 @@ __global__ void pack_rows_kernel(int M, const U* __restrict__ src, const int64_t
         const int col = c0 + e;
         U v = U(0);
         if (col >= a && col < b) v = src[so + (col - a)];
-        dst[p0 + e] = v;
+        dst[p0 + e] = bias(v);
     }
 }
 
@@ -82,6 +91,49 @@ extern "C" const char* viprs_b200_strerror(int code) {
     return "unknown error";
 }
 
+namespace vb {
+
+// bytes of dynamic shared memory the sweep needs besides the TMA ring
+static int state_bytes(int max_block, int tsize) {
+    return (int)make_layout(state_pad(max_block), tsize, 0, 0).total;
+}
+
+RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize) {
+    RingGeometry g{0, 0, 0};
+    const int st = state_bytes(ld->max_block, tsize);
+    const int cap1 = ld->smem_optin;
+    int nst2 = (kSmemTwoPerSM - st) / ld->stage_bytes;
+    int nst1 = (cap1 - st) / ld->stage_bytes;
+    if (nst2 > NST_MAX) nst2 = NST_MAX;
+    if (nst1 > NST_MAX) nst1 = NST_MAX;
+    if (nst2 >= 4) { g.nst = nst2; g.ctas_per_sm = 2; }
+    else if (nst1 >= 3) { g.nst = nst1; g.ctas_per_sm = 1; }
+    else return g;
+    g.smem_bytes = (int)make_layout(state_pad(ld->max_block), tsize, ld->stage_bytes, g.nst).total;
+    return g;
+}
+
+// pick the TMA stage size: four stages next to the float32 block state if two CTAs can share an SM,
+// otherwise four stages of a single CTA per SM; never smaller than the longest packed row.
+static int choose_stage_bytes(int max_block, int max_row_bytes, int smem_optin, int requested) {
+    const char* env = getenv("VIPRS_B200_STAGE_BYTES");
+    if (requested <= 0 && env) requested = atoi(env);
+    int sb;
+    if (requested > 0) {
+        sb = requested;
+    } else {
+        const int st = state_bytes(max_block, 4);
+        sb = (kSmemTwoPerSM - st) / 4;
+        if (sb < max_row_bytes || sb < 2048) sb = (smem_optin - st) / 4;
+        if (sb > 48 * 1024) sb = 48 * 1024;
+    }
+    sb &= ~127;
+    if (sb < max_row_bytes) sb = (max_row_bytes + 127) & ~127;
+    return sb;
+}
+
+}  // namespace vb
+
 extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int32_t* left_bound,
                                     const void* indptr, int32_t indptr_is_i64, const void* ld_data,
                                     int32_t ld_dtype, int32_t mem_kind, int32_t stage_bytes, void* stream_) {
@@ -91,8 +143,6 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
     if (viprs_b200_device_count() <= 0) return VIPRS_B200_ENODEVICE;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int epv = 16 / esize;
-    if (stage_bytes <= 0) stage_bytes = vb::kDefaultStageBytes;
-    stage_bytes &= ~15;
 
     int rc = VIPRS_B200_OK;
     viprs_b200_ld* h = new (std::nothrow) viprs_b200_ld();
@@ -145,43 +195,72 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         blk_row.push_back(M);
         const int nb = (int)blk_row.size() - 1;
 
-        // ---- aligned packed rows, panels ----------------------------------------------------
-        std::vector<int32_t> blk_panel(nb + 1), panel_row;
+        // ---- aligned packed rows ------------------------------------------------------------
         std::vector<int64_t> blk_cost(nb);
         int64_t off = 0;
-        int32_t max_block = 0;
+        int32_t max_block = 0, max_row_bytes = 0;
         for (int b = 0; b < nb; ++b) {
             const int r0 = blk_row[b], r1 = blk_row[b + 1];
             max_block = std::max(max_block, r1 - r0);
-            blk_panel[b] = (int32_t)panel_row.size();
-            int64_t pbytes = 0; int prows = 0; int64_t cost = 0;
+            int64_t cost = 0;
             for (int j = r0; j < r1; ++j) {
                 int32_t a = r0 + ((cs[j] - r0) / epv) * epv;
                 int32_t e = r0 + ((ce[j] - r0 + epv - 1) / epv) * epv;
                 if (ce[j] == cs[j]) { e = a; }
                 pcs[j] = a; prow[j] = off;
-                const int64_t rb = (int64_t)(e - a) * esize;
-                if (rb > stage_bytes) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
-                if (prows == 0 || prows == vb::PMAX || pbytes + rb > stage_bytes) {
-                    panel_row.push_back(j); prows = 0; pbytes = 0;
-                }
-                ++prows; pbytes += rb; off += (e - a); cost += (e - a) + 64;
+                max_row_bytes = std::max<int32_t>(max_row_bytes, (e - a) * esize);
+                off += (e - a); cost += (int64_t)(e - a) * esize + 256;
             }
             blk_cost[b] = cost;
         }
         prow[M] = off;
+
+        CUDA_TRY(cudaGetDevice(&h->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        h->M = M; h->ld_dtype = ld_dtype; h->esize = esize; h->epv = epv; h->nnz = nnz;
+        h->packed_elems = off; h->n_blocks = nb; h->max_block = max_block; h->max_row_bytes = max_row_bytes;
+        h->h_blk_row = blk_row;
+        stage_bytes = vb::choose_stage_bytes(max_block, max_row_bytes, h->smem_optin, stage_bytes);
+        h->stage_bytes = stage_bytes;
+        if (vb::ring_geometry(h, 4).nst == 0) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
+
+        // ---- row panels (one TMA bulk copy each) and the chain warp's axpy prerequisites --------
+        std::vector<int32_t> blk_panel(nb + 1), panel_row, panel_need;
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = blk_row[b], r1 = blk_row[b + 1];
+            const int first_panel = (int)panel_row.size();
+            blk_panel[b] = first_panel;
+            int64_t pbytes = 0; int prows = 0;
+            for (int j = r0; j < r1; ++j) {
+                const int64_t rb = (prow[j + 1] - prow[j]) * esize;
+                if (prows == 0 || prows == vb::PMAX || pbytes + rb > stage_bytes) {
+                    panel_row.push_back(j); prows = 0; pbytes = 0;
+                }
+                ++prows; pbytes += rb;
+            }
+            // panel u = rows [ps, pe): its columns need the bulk axpy of every row <= pe-1-WIN, i.e. of
+            // every panel up to the one holding that row (which always ends before ps because PMAX <= WIN/2)
+            const int np_b = (int)panel_row.size() - first_panel;
+            int pc = 0;
+            for (int u = 0; u < np_b; ++u) {
+                const int pe = (u + 1 < np_b) ? panel_row[first_panel + u + 1] : r1;
+                const int need_row = pe - 1 - vb::WIN;          // global row index, may be < r0
+                int need = 0;
+                if (need_row >= r0) {
+                    while (pc + 1 < np_b && panel_row[first_panel + pc + 1] <= need_row) ++pc;
+                    need = pc + 1;
+                }
+                panel_need.push_back(need);
+            }
+        }
         blk_panel[nb] = (int32_t)panel_row.size();
         const int np = (int)panel_row.size();
         panel_row.push_back(M);
+        h->n_panels = np;
 
         std::vector<int32_t> order(nb);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return blk_cost[a] > blk_cost[b]; });
-
-        h->M = M; h->ld_dtype = ld_dtype; h->esize = esize; h->epv = epv; h->nnz = nnz;
-        h->packed_elems = off; h->n_blocks = nb; h->max_block = max_block; h->n_panels = np;
-        h->stage_bytes = stage_bytes; h->h_blk_row = blk_row;
-        CUDA_TRY(cudaGetDevice(&h->device));
 
         // ---- device arrays ------------------------------------------------------------------
         CUDA_TRY(cudaMalloc(&h->d_packed, (size_t)std::max<int64_t>(off, 16) * esize + 64));
@@ -190,6 +269,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMalloc(&h->d_blk_row, sizeof(int32_t) * (nb + 1)));
         CUDA_TRY(cudaMalloc(&h->d_blk_panel, sizeof(int32_t) * (nb + 1)));
         CUDA_TRY(cudaMalloc(&h->d_panel_row, sizeof(int32_t) * (np + 1)));
+        CUDA_TRY(cudaMalloc(&h->d_panel_need, sizeof(int32_t) * std::max(np, 1)));
         CUDA_TRY(cudaMalloc(&h->d_blk_order, sizeof(int32_t) * nb));
         CUDA_TRY(cudaMalloc(&d_src_off, sizeof(int64_t) * (size_t)M));
         CUDA_TRY(cudaMalloc(&d_cs, sizeof(int32_t) * (size_t)M));
@@ -199,6 +279,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMemcpyAsync(h->d_blk_row, blk_row.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_blk_panel, blk_panel.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_panel_row, panel_row.data(), sizeof(int32_t) * (np + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_panel_need, panel_need.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_blk_order, order.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(int64_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_cs, cs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
@@ -249,7 +330,7 @@ fail:
 extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     if (!h) return VIPRS_B200_OK;
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
-    cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_blk_order);
+    cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);
     delete h;
     return VIPRS_B200_OK;
 }

@@ -13,26 +13,31 @@ struct viprs_b200_ld {
     int64_t packed_elems = 0;   // elements in the aligned device layout
     int32_t n_blocks = 0;
     int32_t max_block = 0;      // rows of the largest LD block
+    int32_t max_row_bytes = 0;  // longest packed row
     int32_t n_panels = 0;
     int32_t stage_bytes = 0;
     int device = 0;
+    int smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
 
     // device arrays
-    void* d_packed = nullptr;      // [packed_elems] LD entries, row-major, rows 16B-aligned
+    void* d_packed = nullptr;      // [packed_elems] LD entries (biased integer codes), rows 16B-aligned
     int64_t* d_prow = nullptr;     // [M+1] element offset of each packed row (multiple of epv)
     int32_t* d_pcs = nullptr;      // [M]   first column (global index) of the packed row, aligned
                                    //       to epv relative to the block start
     int32_t* d_blk_row = nullptr;  // [n_blocks+1] first row of every LD block
     int32_t* d_blk_panel = nullptr;// [n_blocks+1] first panel of every LD block
     int32_t* d_panel_row = nullptr;// [n_panels+1] first row of every panel
+    int32_t* d_panel_need = nullptr;// [n_panels] panels of the block whose forward axpy must be complete
+                                   //       before the chain warp may start this panel
     int32_t* d_blk_order = nullptr;// [n_blocks] block ids, most expensive first (LPT schedule)
 
     std::vector<int32_t> h_blk_row;  // host copy for callers (sharding across GPUs)
 };
 
 namespace vb {
-constexpr int kDefaultStageBytes = 20 * 1024;
-// dynamic shared memory the sweep kernel needs for a matrix whose largest block has `max_block`
-// rows, with state type of `tsize` bytes (see sweep.cuh for the carve-up)
-size_t sweep_smem_bytes(int max_block, int epv, int tsize, int stage_bytes, int n_bulk_warps);
+// shared memory per CTA that lets two CTAs share one SM (228 KB per SM, 1 KB reserved per CTA)
+constexpr int kSmemTwoPerSM = 113 * 1024;
+struct RingGeometry { int nst; int smem_bytes; int ctas_per_sm; };
+// ring depth / dynamic shared memory of the sweep for a state type of `tsize` bytes; nst == 0: does not fit
+RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize);
 }  // namespace vb

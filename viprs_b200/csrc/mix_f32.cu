@@ -1,0 +1,11 @@
+// viprs_b200 -- C ABI entry points (include/viprs_b200.h): sparse-mixture sweep, float32 state.
+#include "launch.cuh"
+
+extern "C" int viprs_b200_e_step_mixture_f32(const viprs_b200_ld_t* ld, int32_t K, const float* std_beta,
+                                             float* var_gamma, float* var_mu, float* eta, float* q, float* eta_diff,
+                                             const float* log_null_pi, const float* u_logs,
+                                             const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
+                                             int32_t materialize_q, void* stream) {
+    return vb::mixture_dispatch<float>(ld, K, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
+                                       sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, (cudaStream_t)stream);
+}

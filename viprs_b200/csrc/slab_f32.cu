@@ -1,0 +1,15 @@
+// viprs_b200 -- C ABI entry points (include/viprs_b200.h): spike-and-slab sweep, float32 state.
+#include "launch.cuh"
+
+extern "C" int viprs_b200_e_step_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
+                                     float* var_mu, float* eta, float* q, float* eta_diff, const float* u_logs,
+                                     const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
+                                     int32_t materialize_q, void* stream) {
+    return vb::e_step_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs,
+                                      sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, (cudaStream_t)stream);
+}
+
+extern "C" int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float* q, float dq_scale,
+                                           void* stream) {
+    return vb::backward_dispatch<float>(ld, x, q, dq_scale, (cudaStream_t)stream);
+}

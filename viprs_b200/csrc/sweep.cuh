@@ -1,97 +1,199 @@
-// viprs_b200 -- the one-pass Gauss-Seidel sweep (spike-and-slab CAVI E-step) for sm_100a.
+// viprs_b200 -- the one-pass Gauss-Seidel sweep (CAVI E-step) for sm_100a.
 //
-// Replaces e_step<T,U,I> + update_q_factor<T,U,I> of the reference
-// (/root/reference/viprs/model/vi/e_step.hpp:343-442 and :307-338), threads=1 order.
+// Replaces e_step<T,U,I> / e_step_mixture<T,U,I> + update_q_factor<T,U,I> of the reference
+// (/root/reference/viprs/model/vi/e_step.hpp:343-442, 447-551 and 307-338), threads=1 order.
 //
-// One CTA owns one LD block (rows r0..r1 that only reach columns inside [r0, r1)), keeps the
-// strictly sequential per-SNP update order, and reads every LD entry ONCE:
+// One CTA owns one LD block (rows r0..r1 that only reach columns inside [r0, r1)), keeps the strictly
+// sequential per-SNP update order, and reads every LD entry ONCE from HBM:
 //
 //   q_j used at step j  =  dq * ( F_j + B_j ),
-//       F_j = sum_{i<j} R_ij eta_i(new)     "forward"  -- axpy of finished rows into f_s[]
+//       F_j = sum_{i<j} R_ij eta_i(new)     "forward"  -- axpy of finished rows
 //       B_j = sum_{k>j} R_jk eta_k(old)     "backward" -- dot of row j with the not-yet-updated etas
 //
-// which is algebraically what the reference's incrementally maintained q holds at step j
-// (its second pass, update_q_factor, is exactly the B_j term deferred to the end of the sweep).
+// which is algebraically what the reference's incrementally maintained q holds at step j (its second
+// pass, update_q_factor, is exactly the B_j term deferred to the end of the sweep).
 //
-// Warp roles (CTA = 2 + NBW warps):
-//   warp 0  chain    : per-SNP scalar update, 32-lane register window covering the current panel's
-//                      columns and the next panel's (in-window axpy via one FMA per step)
-//   warp 1  producer : one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per row panel into a
-//                      NSTAGE-deep shared-memory ring; writes the per-row metadata of the stage
-//   warps 2.. bulk   : iteration u = { A(u): B_j for the rows of panel u ; C(u-2): axpy of panel
-//                      u-2's finished rows into f_s[] for columns >= start of panel u }
-// Hand-offs are mbarriers: full/empty (TMA ring), bulk_done (A(u),C(u-2) -> chain(u)),
-// chain_done (eta_new of panel p -> C(p)).  No __syncthreads after the prologue.
+// Warp roles (CTA = 2 + NBW warps, no __syncthreads after the prologue):
+//   warp 0  chain    : per-SNP scalar update, one row panel (1..16 rows) per hand-shake.  Lane l owns the block-local columns
+//                      c == l (mod 32) of a sliding 64-column window (X0: column in (j, j+32], X1: +32):
+//                      the forward axpy of row j into columns < cut_j = ceil((j+33)/EPV)*EPV is one/two
+//                      FMAs per lane per step on register accumulators, so the serial dependence between
+//                      consecutive SNPs never leaves the warp (one SHFL per step).
+//   warp 1  producer : one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per row panel into an NST-deep
+//                      shared-memory ring, plus cp.async.bulk.prefetch.L2 a few panels further ahead;
+//                      writes the per-row metadata ring.
+//   warps 2.. bulk   : A(u): B_j for the rows of panel u (full-row dots against eta_old in shared memory);
+//                      C(v): axpy of panel v's finished rows into f_s[] for columns >= cut_j.
+// Hand-offs: full/empty mbarriers (TMA ring), and three monotonic release/acquire counters in shared
+// memory: a_count (A(u) done, per warp), c_count (C(v) done, per warp), rows_done (chain progress).
 #pragma once
 #include "common.cuh"
 
 namespace vb {
 
-template <typename T>
-struct SweepParams {
-    const void* packed;
-    const int64_t* prow;
-    const int32_t* pcs;
-    const int32_t* blk_row;
-    const int32_t* blk_panel;
-    const int32_t* panel_row;
-    const int32_t* blk_order;
-    int n_blocks;
-    int stage_bytes;
-    int bpad;                 // elements of T in each shared state array
-    const T* std_beta;
-    T* var_gamma;
-    T* var_mu;
-    T* eta;
-    T* q;
-    T* eta_diff;
-    const T* u_logs;
-    const T* sqrt_half_var_tau;
-    const T* mu_mult;
-    T dq_scale;
-};
-
-// shared-memory carve-up (all offsets 16-byte aligned)
+// shared-memory carve-up (byte offsets from the dynamic shared memory base, all 16-byte aligned)
 struct SmemLayout {
-    size_t stages, eta, f, rowmeta, panelmeta, partial, alpha, bars, total;
+    uint32_t stages, eta, f, rowmeta, panelmeta, partial, alpha, bars, counters, total;
 };
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-__host__ __device__ inline SmemLayout make_layout(int bpad, int tsize, int stage_bytes, int nbw) {
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+__host__ __device__ inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
+inline int state_pad(int max_block) { return ((max_block + 63) / 64) * 64 + 64; }
+inline SmemLayout make_layout(int bpad, int tsize, int stage_bytes, int nst) {
     SmemLayout L;
-    size_t o = 0;
-    L.stages = o;    o += (size_t)NSTAGE * stage_bytes;
-    L.eta = o;       o += align16((size_t)bpad * tsize);
-    L.f = o;         o += align16((size_t)bpad * tsize);
-    L.rowmeta = o;   o += (size_t)NSTAGE * PMAX * sizeof(int4);
-    L.panelmeta = o; o += (size_t)NSTAGE * sizeof(int4);
-    L.partial = o;   o += align16((size_t)NSLOT * nbw * PMAX * tsize);
-    L.alpha = o;     o += align16((size_t)NSLOT * PMAX * tsize);
-    L.bars = o;      o += (size_t)(2 * NSTAGE + 2 * NSLOT) * sizeof(uint64_t);
+    uint32_t o = 0;
+    L.stages = o;    o += (uint32_t)nst * (uint32_t)stage_bytes;       o = align128(o);
+    L.eta = o;       o += align16((uint32_t)bpad * tsize);
+    L.f = o;         o += align16((uint32_t)bpad * tsize);
+    L.rowmeta = o;   o += RR * (uint32_t)sizeof(int4);
+    L.panelmeta = o; o += NST_MAX * (uint32_t)sizeof(int4);
+    L.partial = o;   o += align16((uint32_t)NBW * RR * tsize);
+    L.alpha = o;     o += align16((uint32_t)RR * tsize);
+    L.bars = o;      o += 2 * NST_MAX * (uint32_t)sizeof(uint64_t);
+    L.counters = o;  o += 16;
     L.total = o;
     return L;
 }
-inline int state_pad(int max_block) { return ((max_block + 15) / 16) * 16 + 16; }
 
-template <typename T, typename U, int NBW>
-__global__ void __launch_bounds__((NBW + 2) * WARP) sweep_kernel(const SweepParams<T> p) {
+struct SweepPlan {                 // what ld.cu prepared (device pointers) + the ring geometry
+    const unsigned char* packed;
+    const int64_t* prow;           // [M+1] element offset of each packed row
+    const int32_t* pcs;            // [M]   first (aligned) column of each packed row, global index
+    const int32_t* blk_row;        // [n_blocks+1]
+    const int32_t* blk_panel;      // [n_blocks+1]
+    const int32_t* panel_row;      // [n_panels+1]
+    const int32_t* blk_order;      // [n_blocks] LPT order
+    const int32_t* panel_need;     // [n_panels] panels of the block that must be C-complete before the chain
+                                   //            warp starts this panel (rows <= last row of the panel - WIN)
+    int n_blocks;
+    int stage_bytes;
+    int nst;
+    int bpad;
+    int l2_ahead;                  // panels of L2 prefetch distance beyond the ring
+    SmemLayout L;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-SNP update models (the chain warp's scalar math)
+// ---------------------------------------------------------------------------------------------
+// Spike-and-slab, e_step.hpp:397-431.
+template <typename T>
+struct SlabModel {
+    struct Args {
+        const T* std_beta; const T* u_logs; const T* sqrt_half_var_tau; const T* mu_mult;
+        T* var_gamma; T* var_mu; T dq;
+    };
+    struct Lane { T c0, c1, sv, ul; };
+    struct Out { T mu, g; };
+    static __device__ __forceinline__ void load(const Args& a, int row, bool ok, Lane& L) {
+        T beta = T(0), mm = T(0);
+        L.sv = T(0); L.ul = T(0);
+        if (ok) { beta = a.std_beta[row]; mm = a.mu_mult[row]; L.sv = a.sqrt_half_var_tau[row]; L.ul = a.u_logs[row]; }
+        L.c0 = mm * beta;            // mu = fma(mu_mult, beta, -mu_mult*q)   (:401)  with q = dq * X
+        L.c1 = -(mm * a.dq);
+    }
+    // X: F_j + B_j in LD-code units; eo: eta_j before the update
+    static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
+        const T mu = fma_t(L.c1, X, L.c0);
+        const T uu = L.sv * mu;                                   // :404
+        const T g = sigmoid_t(fma_t(uu, uu, L.ul));               // :405
+        d = fma_t(g, mu, -eo);                                    // :408
+        skip = abs_t(d) < eps;                                    // :410-413
+        en = skip ? eo : eo + d;                                  // :431
+        if (skip) d = T(0);
+        o.mu = mu; o.g = g;
+    }
+    static __device__ __forceinline__ void store(const Args& a, int row, bool skip, const Out& o) {
+        if (!skip) { a.var_mu[row] = o.mu; a.var_gamma[row] = o.g; }            // :416-418
+    }
+};
+
+// Sparse mixture (K slabs + null), e_step.hpp:501-536.  (M,K) arrays are C-order; K <= KMAX.
+template <typename T, int KMAX>
+struct MixModel {
+    struct Args {
+        const T* std_beta; const T* u_logs; const T* sqrt_half_var_tau; const T* mu_mult; const T* log_null_pi;
+        T* var_gamma; T* var_mu; T dq; int K;
+    };
+    struct Lane { T beta, lnp; T mm[KMAX], sv[KMAX], ul[KMAX]; int K; T dq; };
+    struct Out { T mu[KMAX], g[KMAX]; };
+    static __device__ __forceinline__ void load(const Args& a, int row, bool ok, Lane& L) {
+        L.K = a.K; L.dq = a.dq;
+        L.beta = ok ? a.std_beta[row] : T(0);
+        L.lnp = ok ? a.log_null_pi[row] : T(0);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const bool v = ok && k < a.K;
+            const size_t m = (size_t)row * a.K + k;
+            L.mm[k] = v ? a.mu_mult[m] : T(0);
+            L.sv[k] = v ? a.sqrt_half_var_tau[m] : T(0);
+            L.ul[k] = v ? a.u_logs[m] : T(0);
+        }
+    }
+    static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
+        (void)eps;
+        const T r = L.beta - L.dq * X;                            // :505
+        T u[KMAX];
+        T mx = L.lnp;                                             // :515, c_max :58-71
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            o.mu[k] = L.mm[k] * r;                                // :509
+            const T t = L.sv[k] * o.mu[k];                        // :510
+            u[k] = fma_t(t, t, L.ul[k]);                          // :511
+            if (k < L.K) mx = u[k] > mx ? u[k] : mx;
+        }
+        T sum = exp_t(L.lnp - mx);                                // softmax :222-241
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            u[k] = (k < L.K) ? exp_t(u[k] - mx) : T(0);
+            sum += u[k];
+        }
+        const T inv = rcp_t(sum);
+        d = -eo;                                                  // :519
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            o.g[k] = u[k] * inv;
+            d = fma_t(o.g[k], o.mu[k], d);                        // :523
+        }
+        skip = false;                                             // no skip branch in the mixture sweep
+        en = eo + d;                                              // :536
+    }
+    static __device__ __forceinline__ void store(const Args& a, int row, bool skip, const Out& o) {
+        (void)skip;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < a.K) { a.var_mu[(size_t)row * a.K + k] = o.mu[k]; a.var_gamma[(size_t)row * a.K + k] = o.g[k]; }
+    }
+};
+
+template <typename T> __device__ __forceinline__ T eps_of();
+template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920928955078125e-7f; }   // max(FLT_EPSILON, 1e-8)
+template <> __device__ __forceinline__ double eps_of<double>() { return 1e-8; }                    // max(DBL_EPSILON, 1e-8)
+
+template <typename T>
+struct StateArgs { T* eta; T* q; T* eta_diff; };
+
+// ---------------------------------------------------------------------------------------------
+// the sweep kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename U, typename Model, int MINB>
+__global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const SweepPlan p, const typename Model::Args ma,
+                                                                 const StateArgs<T> sa) {
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int ES = (int)sizeof(U);
-    constexpr int NBT = NBW * WARP;
+    constexpr int TPV = EPV * (int)sizeof(T) / 16;       // 16-byte chunks of state per LD vector
     extern __shared__ __align__(128) unsigned char smem[];
 
-    const SmemLayout L = make_layout(p.bpad, (int)sizeof(T), p.stage_bytes, NBW);
-    unsigned char* stages = smem + L.stages;
-    T* eta_s = reinterpret_cast<T*>(smem + L.eta);
-    T* f_s = reinterpret_cast<T*>(smem + L.f);
-    int4* rowmeta = reinterpret_cast<int4*>(smem + L.rowmeta);      // [NSTAGE][PMAX] {rowbase, vs, ve, -}
-    int4* panelmeta = reinterpret_cast<int4*>(smem + L.panelmeta);  // [NSTAGE] {P, vmin, vmax, bytes}
-    T* partial = reinterpret_cast<T*>(smem + L.partial);            // [NSLOT][NBW][PMAX]
-    T* alpha = reinterpret_cast<T*>(smem + L.alpha);                // [NSLOT][PMAX]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + NSTAGE;
-    uint64_t* bulk_done = bars + 2 * NSTAGE;
-    uint64_t* chain_done = bars + 2 * NSTAGE + NSLOT;
+    T* eta_s = reinterpret_cast<T*>(smem + p.L.eta);
+    T* f_s = reinterpret_cast<T*>(smem + p.L.f);
+    int4* rowmeta = reinterpret_cast<int4*>(smem + p.L.rowmeta);      // [RR] {byte offset of column 0, vs, ve, -}
+    int4* panelmeta = reinterpret_cast<int4*>(smem + p.L.panelmeta);  // [NST] {P, vmin, vmax, first local row}
+    T* partial = reinterpret_cast<T*>(smem + p.L.partial);            // [NBW][RR]
+    T* alpha = reinterpret_cast<T*>(smem + p.L.alpha);                // [RR]  eta_new of finished rows
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
+    uint64_t* empty = full + NST_MAX;
+    uint32_t* a_count = reinterpret_cast<uint32_t*>(smem + p.L.counters);
+    uint32_t* c_count = a_count + 1;
+    uint32_t* rows_done = a_count + 2;
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int blk = p.blk_order[blockIdx.x];
@@ -99,40 +201,48 @@ __global__ void __launch_bounds__((NBW + 2) * WARP) sweep_kernel(const SweepPara
     const int B = r1 - r0;
     const int pan0 = p.blk_panel[blk];
     const int NP = p.blk_panel[blk + 1] - pan0;
+    const int NST = p.nst;
 
     // ---- prologue: state into shared memory, barriers ---------------------------------------
     for (int i = tid; i < p.bpad; i += blockDim.x) {
-        eta_s[i] = (i < B) ? p.eta[r0 + i] : T(0);
+        eta_s[i] = (i < B) ? sa.eta[r0 + i] : T(0);
         f_s[i] = T(0);
     }
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NBW); }
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&bulk_done[s], NBW); mbar_init(&chain_done[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NBW); }
+        *a_count = 0; *c_count = 0; *rows_done = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
     if (warp == 1) {
         // =============================== producer ===========================================
-        const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(p.packed);
+        const unsigned char* gsrc = p.packed;
+        if (lane == 0) {
+            const int npf = min(NP, NST + p.l2_ahead);
+            for (int v = NST; v < npf; ++v) {
+                const int64_t o0 = p.prow[p.panel_row[pan0 + v]], o1 = p.prow[p.panel_row[pan0 + v + 1]];
+                if (o1 > o0) tma_prefetch_l2(gsrc + o0 * ES, (uint32_t)((o1 - o0) * ES));
+            }
+        }
         for (int v = 0; v < NP; ++v) {
-            const int s = v % NSTAGE, k = v / NSTAGE;
-            if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+            const int s = v % NST, k = v / NST;
             const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
             const int P = re - rs;
             const int64_t obase = p.prow[rs];
             const int64_t oend = p.prow[re];
+            int64_t o0 = 0, o1 = 0;
+            int c = 0;
+            if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
+            if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
             int vs = 0x7fffffff, ve = 0;
             if (lane < P) {
-                const int row = rs + lane;
-                const int64_t o0 = p.prow[row], o1 = p.prow[row + 1];
-                const int c = p.pcs[row] - r0;           // block-local first column, multiple of EPV
                 const int nv = (int)(o1 - o0) / EPV;
                 const int vs_r = c / EPV;
                 int4 m;
-                m.x = (int)((o0 - obase) * ES) - vs_r * 16;   // stage byte offset of local column 0
+                m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
                 m.y = vs_r; m.z = vs_r + nv; m.w = 0;
-                rowmeta[s * PMAX + lane] = m;
+                rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
                 if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
             }
 #pragma unroll
@@ -141,188 +251,216 @@ __global__ void __launch_bounds__((NBW + 2) * WARP) sweep_kernel(const SweepPara
                 ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
             }
             const uint32_t bytes = (uint32_t)((oend - obase) * ES);
-            if (lane == 0) panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, (int)bytes);
+            if (lane == 0) panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
             __syncwarp();
             if (lane == 0) {
                 if (bytes > 0) {
                     mbar_arrive_expect_tx(&full[s], bytes);
-                    tma_load_1d(stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
+                    tma_load_1d(smem + p.L.stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
                 } else {
                     mbar_arrive(&full[s]);
+                }
+                const int vp = v + NST + p.l2_ahead;
+                if (vp < NP) {
+                    const int64_t q0 = p.prow[p.panel_row[pan0 + vp]], q1 = p.prow[p.panel_row[pan0 + vp + 1]];
+                    if (q1 > q0) tma_prefetch_l2(gsrc + q0 * ES, (uint32_t)((q1 - q0) * ES));
                 }
             }
         }
     } else if (warp == 0) {
         // =============================== chain ==============================================
-        const T eps = (sizeof(T) == 4) ? T(1.1920928955078125e-7) : T(1e-8);   // e_step.hpp:382
-        const T dq = p.dq_scale;
-        T carried = T(0);
-        for (int pn = 0; pn < NP; ++pn) {
-            const int s = pn % NSTAGE, slot = pn % NSLOT;
-            const int rs = p.panel_row[pan0 + pn], re = p.panel_row[pan0 + pn + 1];
-            const int P = re - rs;
-            const int cut2 = ((pn + 1 < NP) ? p.panel_row[pan0 + pn + 2] : re) - r0;
-            const int row = rs + lane;
-            const bool valid = lane < P;
-            T beta = T(0), mm = T(0), sv = T(0), ul = T(0), eo = T(0);
-            if (valid) {
-                beta = p.std_beta[row]; mm = p.mu_mult[row]; sv = p.sqrt_half_var_tau[row];
-                ul = p.u_logs[row]; eo = p.eta[row];
-            }
-            mbar_wait(&bulk_done[slot], (pn / NSLOT) & 1);
+        const T eps = eps_of<T>();
+        const T dq = ma.dq;
+        typename Model::Lane L;
+        Model::load(ma, r0 + lane, lane < B, L);
+        T eo = (lane < B) ? eta_s[lane] : T(0);
+        T X0 = T(0), X1 = T(0);
+        int j0 = 0;
+        int rs_next = p.panel_row[pan0 + 1] - r0;
+        int need_c = p.panel_need[pan0];
+        for (int u = 0; u < NP; ++u) {
+            // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
+            const int nrows = rs_next - j0;
+            const int base = j0 & 31;
+            const int rel = (lane - base) & 31;
+            const int need_c_cur = need_c;
+            if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
+            wait_ge(a_count, (uint32_t)(NBW * (u + 1)));
+            wait_ge(c_count, (uint32_t)(NBW * need_c_cur));
 
+            // fold what the bulk warps prepared for this batch's 16 columns
             T bsum = T(0);
-            if (valid) {
+            if (rel < nrows) {
+                const int cl = j0 + rel;
 #pragma unroll
-                for (int w = 0; w < NBW; ++w) bsum += partial[(slot * NBW + w) * PMAX + lane];
+                for (int w = 0; w < NBW; ++w) bsum += partial[w * RR + (cl & (RR - 1))];
+                X0 += f_s[cl] + bsum;
             }
-            T X = valid ? (f_s[row - r0] + carried) : T(0);
-
-            // window coefficients: lane <-> local column col; rows of this panel
-            const unsigned char* st = stages + (size_t)s * p.stage_bytes;
-            const int col = (rs - r0) + lane;
-            const int vcol = col / EPV;
-            T w[PMAX];
-#pragma unroll
-            for (int i = 0; i < PMAX; ++i) {
-                w[i] = T(0);
-                if (i < P) {
-                    const int4 m = rowmeta[s * PMAX + i];
-                    if (col > (rs - r0) + i && col < cut2 && vcol >= m.y && vcol < m.z)
-                        w[i] = ld_elem<T, U>(st, m.x + col * ES);
-                }
-            }
-
-            T o_mu = T(0), o_g = T(0), o_d = T(0), o_eta = T(0), o_F = T(0);
+            typename Model::Out o_out;
+            T o_d = T(0), o_en = T(0), o_F = T(0);
             bool o_skip = true;
 #pragma unroll
-            for (int i = 0; i < PMAX; ++i) {
-                if (i < P) {
-                    const T qv = dq * (X + bsum);
-                    const T mu = fma_t(mm, beta, -mm * qv);                 // e_step.hpp:401
-                    const T uu = sv * mu;                                   // :404
-                    const T g = sigmoid_t(fma_t(uu, uu, ul));               // :405
-                    const T d = fma_t(g, mu, -eo);                          // :408
-                    const bool skip = abs_t(d) < eps;                       // :410
-                    const T en = skip ? eo : (eo + d);                      // :431
-                    if (lane == i) { o_mu = mu; o_g = g; o_d = skip ? T(0) : d; o_eta = en; o_F = X; o_skip = skip; }
-                    const T a = shfl_t(en, i);
-                    X = fma_t(w[i], a, X);                                  // :421 restricted to the window
+            for (int h = 0; h < BATCH; h += 8) {
+                T w0[8], w1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int jl = j0 + h + i;                 // block-local row of this step
+                    w0[i] = T(0); w1[i] = T(0);
+                    if (h + i < nrows) {
+                        const int4 m = rowmeta[jl & (RR - 1)];
+                        const int cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
+                        const int c0 = j0 + rel + ((rel <= h + i) ? 32 : 0);
+                        const int c1 = c0 + 32;
+                        if (c0 < cut && c0 / EPV >= m.y && c0 / EPV < m.z) w0[i] = ld_elem<T, U>(smem + m.x + c0 * ES);
+                        if (c1 < cut && c1 / EPV >= m.y && c1 / EPV < m.z) w1[i] = ld_elem<T, U>(smem + m.x + c1 * ES);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (h + i < nrows) {
+                        T en, d;
+                        bool skip;
+                        typename Model::Out o;
+                        Model::step(L, X0, eo, eps, en, d, skip, o);
+                        const bool mine = (rel == h + i);
+                        if (mine) { o_out = o; o_d = d; o_en = en; o_F = X0 - bsum; o_skip = skip; }
+                        const T a = shfl_t(en, (base + h + i) & 31);
+                        if (mine) { X0 = X1; X1 = T(0); }
+                        X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
+                        X1 = fma_t(w1[i], a, X1);
+                    }
                 }
             }
-            if (valid) {
-                if (!o_skip) { p.var_mu[row] = o_mu; p.var_gamma[row] = o_g; p.eta[row] = o_eta; }   // :416-418,431
-                p.eta_diff[row] = o_d;
-                p.q[row] = dq * o_F;
-                alpha[slot * PMAX + lane] = o_eta;
+            // batch epilogue: outputs of the 16 rows, eta_new for the bulk axpy, parameters of the lanes' next columns
+            if (rel < nrows) {
+                const int cl = j0 + rel;
+                const int row = r0 + cl;
+                Model::store(ma, row, o_skip, o_out);
+                if (!o_skip) sa.eta[row] = o_en;                                   // :431
+                sa.eta_diff[row] = o_d;                                            // :413 / :418
+                sa.q[row] = dq * o_F;                                              // forward part of q (see header)
+                alpha[cl & (RR - 1)] = o_en;
             }
-            carried = shfl_down_t(X, P);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&chain_done[slot]);
+            if (lane == 0) st_release(rows_done, (uint32_t)(j0 + nrows));
+            if (rel < nrows) {
+                const int cn = j0 + rel + 32;
+                Model::load(ma, r0 + cn, cn < B, L);
+                eo = (cn < B) ? eta_s[cn] : T(0);
+            }
+            j0 += nrows;
         }
     } else {
         // =============================== bulk ===============================================
         const int wb = warp - 2;
         const int tb = wb * WARP + lane;
+        int cnext = 0;                                     // next panel whose axpy (C) this warp has to do
+
+        auto do_C = [&](int v) {
+            const int sc = v % NST;
+            const int4 pm = panelmeta[sc];
+            const int Pc = pm.x, vmaxc = pm.z, jl0 = pm.w;
+            const int first = (jl0 + WIN + EPV - 1) / EPV;
+            int vv = first + (((tb - first) % NBT) + NBT) % NBT;       // static ownership: vv == tb (mod NBT)
+            for (; vv < vmaxc; vv += NBT) {
+                T fs[EPV];
+                uint4* fp = reinterpret_cast<uint4*>(f_s + (size_t)vv * EPV);
+#pragma unroll
+                for (int e = 0; e < TPV; ++e) {
+                    const uint4 t = fp[e];
+                    memcpy(reinterpret_cast<unsigned char*>(fs) + 16 * e, &t, 16);
+                }
+                for (int rg = 0; rg < Pc; rg += 8) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (rg + r < Pc) {
+                            const int jl = jl0 + rg + r;
+                            const int4 m = rowmeta[jl & (RR - 1)];
+                            const int lo = max(m.y, (jl + WIN + EPV - 1) / EPV);
+                            if (vv >= lo && vv < m.z) {
+                                const uint4 c = *reinterpret_cast<const uint4*>(smem + m.x + vv * 16);
+                                VecOps<T, U>::axpy(c, alpha[jl & (RR - 1)], fs);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < TPV; ++e) {
+                    uint4 t;
+                    memcpy(&t, reinterpret_cast<unsigned char*>(fs) + 16 * e, 16);
+                    fp[e] = t;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                red_release_add(c_count, 1u);
+                mbar_arrive(&empty[sc]);
+            }
+        };
+
         for (int u = 0; u < NP; ++u) {
-            const int s = u % NSTAGE, slot = u % NSLOT;
-            mbar_wait(&full[s], (u / NSTAGE) & 1);
+            const int s = u % NST;
+            // the stage of panel u is only re-filled after C(u - NST): do the overdue axpys first (blocking)
+            while (cnext <= u - NST) {
+                wait_ge(rows_done, (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0));
+                do_C(cnext++);
+            }
+            mbar_wait(&full[s], (u / NST) & 1);
             {
                 // ---- A(u): backward dots of the rows of panel u --------------------------------
                 const int4 pm = panelmeta[s];
-                const int P = pm.x, vmin = pm.y, vmax = pm.z;
-                const unsigned char* st = stages + (size_t)s * p.stage_bytes;
+                const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
                 for (int rg = 0; rg < P; rg += 8) {
-                    T acc[8];
-                    int4 m[8];
+                    typename Pk<T>::acc_t acc2[8];
+                    int mx[8], my[8], mz[8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        acc[r] = T(0);
-                        m[r] = (rg + r < P) ? rowmeta[s * PMAX + rg + r] : make_int4(0, 0, 0, 0);
+                        acc2[r] = Pk<T>::zero();
+                        mx[r] = 0; my[r] = 0; mz[r] = 0;
+                        if (rg + r < P) {
+                            const int4 m = rowmeta[(jl0 + rg + r) & (RR - 1)];
+                            mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                        }
                     }
                     for (int v = vmin + tb; v < vmax; v += NBT) {
                         T es[EPV];
                         const uint4* ep = reinterpret_cast<const uint4*>(eta_s + (size_t)v * EPV);
 #pragma unroll
-                        for (int e = 0; e < (int)(EPV * sizeof(T) / 16); ++e) {
+                        for (int e = 0; e < TPV; ++e) {
                             const uint4 t = ep[e];
                             memcpy(reinterpret_cast<unsigned char*>(es) + 16 * e, &t, 16);
                         }
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            if (v >= m[r].y && v < m[r].z) {
-                                const uint4 c = *reinterpret_cast<const uint4*>(st + m[r].x + v * 16);
-                                T vals[EPV];
-                                Decode<T, U>::vec(c, vals);
-#pragma unroll
-                                for (int e = 0; e < EPV; ++e) acc[r] = fma_t(vals[e], es[e], acc[r]);
+                            if (v >= my[r] && v < mz[r]) {
+                                const uint4 c = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+                                VecOps<T, U>::dot(c, es, acc2[r]);
                             }
                         }
                     }
+                    T acc[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (rg + r < P) {
-                            const T sum = warp_sum(acc[r]);
-                            if (lane == 0) partial[(slot * NBW + wb) * PMAX + rg + r] = sum;
-                        }
-                    }
+                    for (int r = 0; r < 8; ++r) acc[r] = Pk<T>::sum(acc2[r]);
+                    const int rr = warp_reduce8(acc, lane);
+                    if ((lane & 3) == 0 && rg + rr < P) partial[wb * RR + ((jl0 + rg + rr) & (RR - 1))] = acc[0];
                 }
-            }
-            if (u >= 2) {
-                // ---- C(u-2): axpy of panel u-2's finished rows into columns >= start(u) ---------
-                const int pc = u - 2;
-                const int sc = pc % NSTAGE, slotc = pc % NSLOT;
-                mbar_wait(&chain_done[slotc], (pc / NSLOT) & 1);
-                const int4 pm = panelmeta[sc];
-                const int Pc = pm.x, vmaxc = pm.z;
-                const unsigned char* st = stages + (size_t)sc * p.stage_bytes;
-                const int cut = p.panel_row[pan0 + u] - r0;
-                const int vlo = cut / EPV, rem = cut % EPV;
-                int v = vlo + ((tb - vlo) % NBT + NBT) % NBT;      // static ownership: v == tb (mod NBT)
-                for (; v < vmaxc; v += NBT) {
-                    T fs[EPV];
-                    uint4* fp = reinterpret_cast<uint4*>(f_s + (size_t)v * EPV);
-#pragma unroll
-                    for (int e = 0; e < (int)(EPV * sizeof(T) / 16); ++e) {
-                        const uint4 t = fp[e];
-                        memcpy(reinterpret_cast<unsigned char*>(fs) + 16 * e, &t, 16);
-                    }
-                    for (int r = 0; r < Pc; ++r) {
-                        const int4 m = rowmeta[sc * PMAX + r];
-                        if (v >= m.y && v < m.z) {
-                            const uint4 c = *reinterpret_cast<const uint4*>(st + m.x + v * 16);
-                            T vals[EPV];
-                            Decode<T, U>::vec(c, vals);
-                            if (v == vlo && rem) {
-#pragma unroll
-                                for (int e = 0; e < EPV; ++e) if (e < rem) vals[e] = T(0);
-                            }
-                            const T a = alpha[slotc * PMAX + r];
-#pragma unroll
-                            for (int e = 0; e < EPV; ++e) fs[e] = fma_t(vals[e], a, fs[e]);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < (int)(EPV * sizeof(T) / 16); ++e) {
-                        uint4 t;
-                        memcpy(&t, reinterpret_cast<unsigned char*>(fs) + 16 * e, 16);
-                        fp[e] = t;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[sc]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bulk_done[slot]);
+            if (lane == 0) red_release_add(a_count, 1u);
+            // opportunistic axpys: every panel the chain has already finished
+            while (cnext <= u && ld_acquire(rows_done) >= (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0)) do_C(cnext++);
+        }
+        while (cnext < NP) {
+            wait_ge(rows_done, (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0));
+            do_C(cnext++);
         }
     }
 }
 
 // q[j] += dq * sum_{k>j} R_jk x[k]   (update_q_factor, e_step.hpp:307-338); one warp per row.
 template <typename T, typename U>
-__global__ void backward_dot_kernel(int M, const U* __restrict__ packed, const int64_t* __restrict__ prow,
-                                    const int32_t* __restrict__ pcs, const T* __restrict__ x,
-                                    T* __restrict__ q, T dq) {
+__global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ packed, const int64_t* __restrict__ prow,
+                                    const int32_t* __restrict__ pcs, const T* __restrict__ x, T* __restrict__ q, T dq) {
     constexpr int EPV = LdTraits<U>::EPV;
     const int row = blockIdx.x * (blockDim.x / WARP) + threadIdx.x / WARP;
     if (row >= M) return;
@@ -330,20 +468,17 @@ __global__ void backward_dot_kernel(int M, const U* __restrict__ packed, const i
     const int64_t o0 = prow[row];
     const int nv = (int)((prow[row + 1] - o0) / EPV);
     const int c0 = pcs[row];
-    const uint4* src = reinterpret_cast<const uint4*>(packed + o0);
-    T acc = T(0);
+    const uint4* src = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
+    typename Pk<T>::acc_t acc2 = Pk<T>::zero();
     for (int v = lane; v < nv; v += WARP) {
         const uint4 c = src[v];
-        T vals[EPV];
-        Decode<T, U>::vec(c, vals);
         const int col = c0 + v * EPV;
+        T xs[EPV];
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-            const T xv = (col + e < M) ? x[col + e] : T(0);
-            acc = fma_t(vals[e], xv, acc);
-        }
+        for (int e = 0; e < EPV; ++e) xs[e] = (col + e < M) ? x[col + e] : T(0);
+        VecOps<T, U>::dot(c, xs, acc2);
     }
-    acc = warp_sum(acc);
+    const T acc = warp_sum(Pk<T>::sum(acc2));
     if (lane == 0 && nv > 0) q[row] += dq * acc;
 }
 

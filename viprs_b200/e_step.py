@@ -53,6 +53,66 @@ def e_step_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqr
     _lib.check(rc, "viprs_b200_e_step")
 
 
+def e_step_mixture_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
+                          sqrt_half_var_tau, mu_mult, dq_scale, materialize_q=True):
+    """One mixture sweep on a DeviceLD; (M,K) arrays are C-order CUDA tensors, the rest have M entries."""
+    L = _lib.lib()
+    dt = var_mu.dtype
+    if var_mu.dim() != 2:
+        raise ValueError("e_step_mixture_device: var_mu must be (M, K)")
+    K = var_mu.shape[1]
+    for t in (var_gamma, var_mu, u_logs, sqrt_half_var_tau, mu_mult):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and tuple(t.shape) == (ld.M, K)):
+            raise ValueError("e_step_mixture_device: (M,K) arrays must be C-contiguous CUDA tensors of one dtype")
+    for t in (std_beta, eta, q, eta_diff, log_null_pi):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == dt and t.numel() == ld.M):
+            raise ValueError("e_step_mixture_device: (M,) arrays must be contiguous CUDA tensors of one dtype")
+    fn = L.viprs_b200_e_step_mixture_f32 if dt == torch.float32 else L.viprs_b200_e_step_mixture_f64
+    rc = fn(ld.handle, K, std_beta.data_ptr(), var_gamma.data_ptr(), var_mu.data_ptr(), eta.data_ptr(), q.data_ptr(),
+            eta_diff.data_ptr(), log_null_pi.data_ptr(), u_logs.data_ptr(), sqrt_half_var_tau.data_ptr(),
+            mu_mult.data_ptr(), float(dq_scale), int(bool(materialize_q)), _stream_ptr())
+    _lib.check(rc, "viprs_b200_e_step_mixture")
+
+
+def _host_index_arrays(ld_left_bound, ld_indptr, ld_data):
+    lb = np.ascontiguousarray(ld_left_bound, dtype=np.int32)
+    ip = np.ascontiguousarray(ld_indptr)
+    if ip.dtype not in (np.int32, np.int64):
+        ip = ip.astype(np.int64)
+    return lb, ip, np.ascontiguousarray(ld_data)
+
+
+def cpp_e_step_mixture(ld_left_bound, ld_indptr, ld_data, std_beta, var_gamma, var_mu, eta, q, eta_diff,
+                       log_null_pi, u_logs, sqrt_half_var_tau, mu_mult, dq_scale, threads=1, low_memory=True):
+    """
+    cpp_e_step_mixture (e_step_cpp.pyx:125-159): (M,K) arrays C-order, K = var_mu.shape[1]; in-place outputs.
+    ``threads`` is accepted and ignored (always the sequential sweep).
+    """
+    if isinstance(ld_data, torch.Tensor):
+        ld = device_ld_for(ld_left_bound, ld_indptr, ld_data)
+        return e_step_mixture_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
+                                     sqrt_half_var_tau, mu_mult, dq_scale, True)
+    L = _lib.lib()
+    M, K = var_mu.shape
+    dt = var_mu.dtype
+    fdt = _FLOAT_DT[dt]
+    lb, ip, ld_data = _host_index_arrays(ld_left_bound, ld_indptr, ld_data)
+    ins = [np.ascontiguousarray(a, dtype=dt) for a in (std_beta, log_null_pi, u_logs, sqrt_half_var_tau, mu_mult)]
+    for a in (var_gamma, var_mu):
+        if not (a.flags["C_CONTIGUOUS"] and a.dtype == dt and a.shape == (M, K)):
+            raise ValueError("cpp_e_step_mixture: var_gamma / var_mu must be C-contiguous (M, K)")
+    for a in (eta, q, eta_diff):
+        if not (a.flags["C_CONTIGUOUS"] and a.dtype == dt and a.shape == (M,)):
+            raise ValueError("cpp_e_step_mixture: eta / q / eta_diff must be C-contiguous (M,)")
+    rc = L.viprs_b200_cpp_e_step_mixture(M, K, lb.ctypes.data, ip.ctypes.data, int(ip.dtype == np.int64),
+                                         ld_data.ctypes.data, _NP_DT[ld_data.dtype], fdt, ins[0].ctypes.data,
+                                         var_gamma.ctypes.data, var_mu.ctypes.data, eta.ctypes.data, q.ctypes.data,
+                                         eta_diff.ctypes.data, ins[1].ctypes.data, ins[2].ctypes.data,
+                                         ins[3].ctypes.data, ins[4].ctypes.data, float(dq_scale), int(threads),
+                                         int(bool(low_memory)))
+    _lib.check(rc, "viprs_b200_cpp_e_step_mixture")
+
+
 def cpp_e_step(ld_left_bound, ld_indptr, ld_data, std_beta, var_gamma, var_mu, eta, q, eta_diff,
                u_logs, sqrt_half_var_tau, mu_mult, dq_scale, threads=1, low_memory=True):
     """

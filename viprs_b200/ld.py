@@ -71,6 +71,8 @@ class DeviceLD:
         self.nnz = info.nnz
         self.packed_elems = info.packed_elems
         self.smem_bytes = info.smem_bytes
+        self.ring_stages = info.ring_stages
+        self.ctas_per_sm = info.ctas_per_sm
         self.elem_size = {0: 1, 1: 2, 2: 4, 3: 8}[info.ld_dtype]
         self.device = torch.device("cuda", torch.cuda.current_device())
 
