@@ -89,6 +89,16 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t target) {
     }
 }
 
+// all NBW per-warp progress counters >= target (called by a full warp; lane w < NBW polls counter w)
+__device__ __forceinline__ void wait_all_ge(const uint32_t* prog, uint32_t target, int lane) {
+    uint32_t spins = 0;
+    for (;;) {
+        const bool ok = (lane >= NBW) || (ld_acquire(prog + lane) >= target);
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // packed fp32x2 math (sm_100: FFMA2 / FADD2 -- two IEEE fp32 operations per issue slot)
 // ---------------------------------------------------------------------------------------------

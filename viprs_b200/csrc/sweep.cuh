@@ -24,8 +24,8 @@
 //                      writes the per-row metadata ring.
 //   warps 2.. bulk   : A(u): B_j for the rows of panel u (full-row dots against eta_old in shared memory);
 //                      C(v): axpy of panel v's finished rows into f_s[] for columns >= cut_j.
-// Hand-offs: full/empty mbarriers (TMA ring), and three monotonic release/acquire counters in shared
-// memory: a_count (A(u) done, per warp), c_count (C(v) done, per warp), rows_done (chain progress).
+// Hand-offs: full/empty mbarriers (TMA ring), and monotonic release/acquire progress counters in shared
+// memory: a_prog[w] / c_prog[w] (panels whose A / C bulk warp w has finished), rows_done (chain progress).
 #pragma once
 #include "common.cuh"
 
@@ -49,7 +49,7 @@ inline SmemLayout make_layout(int bpad, int tsize, int stage_bytes, int nst) {
     L.partial = o;   o += align16((uint32_t)NBW * RR * tsize);
     L.alpha = o;     o += align16((uint32_t)RR * tsize);
     L.bars = o;      o += 2 * NST_MAX * (uint32_t)sizeof(uint64_t);
-    L.counters = o;  o += 16;
+    L.counters = o;  o += (2 * NBW + 4) * (uint32_t)sizeof(uint32_t);
     L.total = o;
     return L;
 }
@@ -191,9 +191,9 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
     T* alpha = reinterpret_cast<T*>(smem + p.L.alpha);                // [RR]  eta_new of finished rows
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
     uint64_t* empty = full + NST_MAX;
-    uint32_t* a_count = reinterpret_cast<uint32_t*>(smem + p.L.counters);
-    uint32_t* c_count = a_count + 1;
-    uint32_t* rows_done = a_count + 2;
+    uint32_t* a_prog = reinterpret_cast<uint32_t*>(smem + p.L.counters);   // [NBW] panels whose A this warp finished
+    uint32_t* c_prog = a_prog + NBW;                                        // [NBW] panels whose C this warp finished
+    uint32_t* rows_done = a_prog + 2 * NBW;                                 // rows the chain warp has retired
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int blk = p.blk_order[blockIdx.x];
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
     }
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NBW); }
-        *a_count = 0; *c_count = 0; *rows_done = 0;
+        for (int w = 0; w < NBW; ++w) { a_prog[w] = 0; c_prog[w] = 0; }
+        *rows_done = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
             const int rel = (lane - base) & 31;
             const int need_c_cur = need_c;
             if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
-            wait_ge(a_count, (uint32_t)(NBW * (u + 1)));
-            wait_ge(c_count, (uint32_t)(NBW * need_c_cur));
+            wait_all_ge(a_prog, (uint32_t)(u + 1), lane);
+            wait_all_ge(c_prog, (uint32_t)need_c_cur, lane);
 
             // fold what the bulk warps prepared for this batch's 16 columns
             T bsum = T(0);
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
             }
             __syncwarp();
             if (lane == 0) {
-                red_release_add(c_count, 1u);
+                st_release(&c_prog[wb], (uint32_t)(v + 1));
                 mbar_arrive(&empty[sc]);
             }
         };
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
                 }
             }
             __syncwarp();
-            if (lane == 0) red_release_add(a_count, 1u);
+            if (lane == 0) st_release(&a_prog[wb], (uint32_t)(u + 1));
             // opportunistic axpys: every panel the chain has already finished
             while (cnext <= u && ld_acquire(rows_done) >= (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0)) do_C(cnext++);
         }
