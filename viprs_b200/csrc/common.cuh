@@ -10,9 +10,10 @@ namespace vb {
 
 constexpr int WARP = 32;
 constexpr int PMAX = 16;        // max rows per panel (one TMA bulk copy)
-constexpr int BATCH = 16;       // rows the chain warp retires between two hand-shakes
-constexpr int RR = 128;         // per-row ring slots (row metadata, dot partials, eta_new); needs NST <= 8
-constexpr int NST_MAX = 8;      // max TMA ring depth
+constexpr int NST_MAX = 4;      // max TMA ring depth
+constexpr int RR = 64;          // per-row ring slots (row metadata, dot partials, eta_new, window coefficients);
+                                // two rows RR apart are never resident together: RR > PMAX * NST_MAX - 1
+constexpr int WW = 48;          // window coefficients kept per row: columns j+1 .. j+WW (cut_j - j - 1 <= 47)
 constexpr int NBW = 8;          // bulk warps per CTA
 constexpr int NBT = NBW * WARP;
 constexpr int WIN = 33;         // row j's forward axpy is done by the chain warp for columns < cut_j,
@@ -37,11 +38,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so the
+// waiting warps do not burn issue slots next to the working ones.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -89,11 +104,13 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t target) {
     }
 }
 
-// all NBW per-warp progress counters >= target (called by a full warp; lane w < NBW polls counter w)
-__device__ __forceinline__ void wait_all_ge(const uint32_t* prog, uint32_t target, int lane) {
+// All 2*NBW per-warp progress counters reached their targets: prog[0..NBW) >= ta, prog[NBW..2NBW) >= tc.
+// Called by a full warp; lane l < 2*NBW polls counter l.
+__device__ __forceinline__ void wait_progress(const uint32_t* prog, uint32_t ta, uint32_t tc, int lane) {
     uint32_t spins = 0;
+    const uint32_t target = lane < NBW ? ta : tc;
     for (;;) {
-        const bool ok = (lane >= NBW) || (ld_acquire(prog + lane) >= target);
+        const bool ok = (lane >= 2 * NBW) || (ld_acquire(prog + lane) >= target);
         if (__all_sync(0xffffffffu, ok)) break;
         if (++spins > kSpinLimit) __trap();
     }
@@ -292,13 +309,34 @@ __device__ __forceinline__ double abs_t(double x) { return fabs(x); }
 __device__ __forceinline__ float rcp_t(float x) { return __frcp_rn(x); }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 
+// rounding-explicit scalar ops (no FMA contraction: the chain warp evaluates the same update twice -- once on
+// the critical path, once for the outputs -- and both must give the same bits)
+__device__ __forceinline__ float mul_t(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_t(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_t(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_t(double a, double b) { return __dadd_rn(a, b); }
+// exp(-|x|) and 1/x on the per-SNP critical path.  float: MUFU.EX2 / MUFU.RCP (<= 2 ulp; the argument scaling
+// adds |x| * 6e-8 relative error to e, i.e. < 3e-7 absolute in gamma) ; double: full precision.
+__device__ __forceinline__ float expneg_t(float ax) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(ax, -1.4426950408889634f)));
+    return r;
+}
+__device__ __forceinline__ double expneg_t(double ax) { return exp(-ax); }
+__device__ __forceinline__ float fast_rcp_t(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ double fast_rcp_t(double x) { return 1.0 / x; }
+
 // stable sigmoid, e_step.hpp:245-261 (two-branch form evaluated branch-free: e = exp(-|x|),
 // x >= 0: 1/(1+e);  x < 0: e/(1+e))
 template <typename T>
 __device__ __forceinline__ T sigmoid_t(T x) {
-    const T e = exp_t(-abs_t(x));
-    const T r = rcp_t(T(1) + e);
-    return x < T(0) ? e * r : r;
+    const T e = expneg_t(abs_t(x));
+    const T num = x < T(0) ? e : T(1);
+    return mul_t(num, fast_rcp_t(add_t(T(1), e)));
 }
 
 template <typename T>
@@ -340,6 +378,28 @@ __device__ __forceinline__ int warp_reduce8(T* acc, int lane) {
     acc[0] += shfl_xor_t(acc[0], 2);
     acc[0] += shfl_xor_t(acc[0], 1);
     return (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+}
+
+// Reduce 4 per-lane accumulators across the warp with 6 shuffles: on return acc[0] of lane l holds the warp
+// total of accumulator  r = 2*bit4(l) + bit3(l).
+template <typename T>
+__device__ __forceinline__ int warp_reduce4(T* acc, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = b4 ? acc[i] : acc[i + 2];
+        const T keep = b4 ? acc[i + 2] : acc[i];
+        acc[i] = keep + shfl_xor_t(send, 16);
+    }
+    {
+        const T send = b3 ? acc[0] : acc[1];
+        const T keep = b3 ? acc[1] : acc[0];
+        acc[0] = keep + shfl_xor_t(send, 8);
+    }
+    acc[0] += shfl_xor_t(acc[0], 4);
+    acc[0] += shfl_xor_t(acc[0], 2);
+    acc[0] += shfl_xor_t(acc[0], 1);
+    return (b4 ? 2 : 0) + (b3 ? 1 : 0);
 }
 
 }  // namespace vb

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "ld.h"
@@ -23,6 +24,7 @@ static int make_plan(const viprs_b200_ld* ld, int tsize, SweepPlan& p, RingGeome
     p.panel_row = ld->d_panel_row; p.blk_order = ld->d_blk_order; p.panel_need = ld->d_panel_need;
     p.n_blocks = ld->n_blocks; p.stage_bytes = ld->stage_bytes; p.nst = g.nst; p.bpad = state_pad(ld->max_block);
     p.l2_ahead = env_int("VIPRS_B200_L2_AHEAD", 8);
+    p.trace = nullptr;
     p.L = make_layout(p.bpad, tsize, ld->stage_bytes, g.nst);
     return VIPRS_B200_OK;
 }
@@ -33,6 +35,21 @@ static int launch_one(const viprs_b200_ld* ld, const SweepPlan& p, const RingGeo
     auto kern = sweep_kernel<T, U, Model, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     if (e != cudaSuccess) return (int)e;
+    const char* trace_path = getenv("VIPRS_B200_TRACE");      // debug only: timeline of CTA 0 of every launch
+    if (trace_path) {
+        SweepPlan pt = p;
+        const size_t nb = (size_t)kTraceSlots * sizeof(unsigned long long);
+        if (cudaMalloc(&pt.trace, nb) != cudaSuccess) return VIPRS_B200_ENOMEM;
+        cudaMemsetAsync(pt.trace, 0, nb, st);
+        kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(pt, ma, sa);
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(kTraceSlots);
+        cudaMemcpy(h.data(), pt.trace, nb, cudaMemcpyDeviceToHost);
+        cudaFree(pt.trace);
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 1, nb, f); fclose(f); }
+        e = cudaGetLastError();
+        return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+    }
     kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(p, ma, sa);
     e = cudaGetLastError();
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
@@ -44,7 +61,9 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
     RingGeometry g;
     int rc = make_plan(ld, (int)sizeof(T), p, g);
     if (rc) return rc;
-    if (g.ctas_per_sm >= 2) return launch_one<T, U, Model, 2>(ld, p, g, ma, sa, st);
+    if constexpr (!Model::kHeavy) {
+        if (g.ctas_per_sm >= 2) return launch_one<T, U, Model, 2>(ld, p, g, ma, sa, st);
+    }
     return launch_one<T, U, Model, 1>(ld, p, g, ma, sa, st);
 }
 

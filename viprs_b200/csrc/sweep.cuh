@@ -13,19 +13,22 @@
 // which is algebraically what the reference's incrementally maintained q holds at step j (its second
 // pass, update_q_factor, is exactly the B_j term deferred to the end of the sweep).
 //
-// Warp roles (CTA = 2 + NBW warps, no __syncthreads after the prologue):
-//   warp 0  chain    : per-SNP scalar update, one row panel (1..16 rows) per hand-shake.  Lane l owns the block-local columns
-//                      c == l (mod 32) of a sliding 64-column window (X0: column in (j, j+32], X1: +32):
-//                      the forward axpy of row j into columns < cut_j = ceil((j+33)/EPV)*EPV is one/two
-//                      FMAs per lane per step on register accumulators, so the serial dependence between
-//                      consecutive SNPs never leaves the warp (one SHFL per step).
-//   warp 1  producer : one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per row panel into an NST-deep
+// Warp roles (CTA = NBW + 2 warps, no __syncthreads after the prologue):
+//   warps 0..NBW-1  bulk : A(u): B_j for the rows of panel u (full-row dots against eta_old in shared
+//                      memory) + the rows' window coefficients; C(v): axpy of panel v's finished rows into
+//                      f_s[] for the columns >= cut_j = ceil((j+33)/EPV)*EPV.
+//   warp NBW     producer: one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per row panel into an NST-deep
 //                      shared-memory ring, plus cp.async.bulk.prefetch.L2 a few panels further ahead;
 //                      writes the per-row metadata ring.
-//   warps 2.. bulk   : A(u): B_j for the rows of panel u (full-row dots against eta_old in shared memory);
-//                      C(v): axpy of panel v's finished rows into f_s[] for columns >= cut_j.
-// Hand-offs: full/empty mbarriers (TMA ring), and monotonic release/acquire progress counters in shared
-// memory: a_prog[w] / c_prog[w] (panels whose A / C bulk warp w has finished), rows_done (chain progress).
+//   warp NBW+1   chain   : the per-SNP scalar update, one row panel (1..16 rows) per hand-shake.  Lane l owns
+//                      the block-local columns c == l (mod 32) of a sliding 64-column window (X0: the column
+//                      in [j, j+32), X1: +32): the forward axpy of row j into the columns < cut_j is two FMAs
+//                      per lane per step on register accumulators, so the serial dependence between
+//                      consecutive SNPs never leaves the warp (one SHFL per step).  It is the highest-numbered
+//                      warp of the CTA (issue priority).
+// Hand-offs: mbarriers full/empty (TMA ring) and cdone (chain finished a panel), all waited on with the
+// hardware-suspending try_wait, plus per-bulk-warp release/acquire progress counters a_prog / c_prog that
+// only the chain warp polls.
 #pragma once
 #include "common.cuh"
 
@@ -33,7 +36,7 @@ namespace vb {
 
 // shared-memory carve-up (byte offsets from the dynamic shared memory base, all 16-byte aligned)
 struct SmemLayout {
-    uint32_t stages, eta, f, rowmeta, panelmeta, partial, alpha, bars, counters, total;
+    uint32_t stages, eta, f, rowmeta, panelmeta, partial, alpha, wwin, bars, counters, total;
 };
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 __host__ __device__ inline uint32_t align128(uint32_t x) { return (x + 127u) & ~127u; }
@@ -48,8 +51,9 @@ inline SmemLayout make_layout(int bpad, int tsize, int stage_bytes, int nst) {
     L.panelmeta = o; o += NST_MAX * (uint32_t)sizeof(int4);
     L.partial = o;   o += align16((uint32_t)NBW * RR * tsize);
     L.alpha = o;     o += align16((uint32_t)RR * tsize);
-    L.bars = o;      o += 2 * NST_MAX * (uint32_t)sizeof(uint64_t);
-    L.counters = o;  o += (2 * NBW + 4) * (uint32_t)sizeof(uint32_t);
+    L.wwin = o;      o += align16((uint32_t)RR * WW * tsize);
+    L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
+    L.counters = o;  o += 2 * NBW * (uint32_t)sizeof(uint32_t);
     L.total = o;
     return L;
 }
@@ -69,8 +73,17 @@ struct SweepPlan {                 // what ld.cu prepared (device pointers) + th
     int nst;
     int bpad;
     int l2_ahead;                  // panels of L2 prefetch distance beyond the ring
+    unsigned long long* trace;     // debug timeline of CTA 0 (VIPRS_B200_TRACE), else null
     SmemLayout L;
 };
+
+// debug timeline of CTA 0: trace[(role * 8 + ev) * kTracePanels + panel] = clock64()   (plain stores, no atomics)
+constexpr int kTracePanels = 4096;
+constexpr int kTraceSlots = 10 * 8 * kTracePanels;
+__device__ __forceinline__ void trace_ev(const SweepPlan& p, int lane, int role, int ev, int panel) {
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && panel < kTracePanels)
+        p.trace[(role * 8 + ev) * kTracePanels + panel] = (unsigned long long)clock64();
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-SNP update models (the chain warp's scalar math)
@@ -82,24 +95,27 @@ struct SlabModel {
         const T* std_beta; const T* u_logs; const T* sqrt_half_var_tau; const T* mu_mult;
         T* var_gamma; T* var_mu; T dq;
     };
+    static constexpr bool kHeavy = false;
+    struct Raw { T beta, mm, sv, ul; };
     struct Lane { T c0, c1, sv, ul; };
     struct Out { T mu, g; };
-    static __device__ __forceinline__ void load(const Args& a, int row, bool ok, Lane& L) {
-        T beta = T(0), mm = T(0);
-        L.sv = T(0); L.ul = T(0);
-        if (ok) { beta = a.std_beta[row]; mm = a.mu_mult[row]; L.sv = a.sqrt_half_var_tau[row]; L.ul = a.u_logs[row]; }
-        L.c0 = mm * beta;            // mu = fma(mu_mult, beta, -mu_mult*q)   (:401)  with q = dq * X
-        L.c1 = -(mm * a.dq);
+    static __device__ __forceinline__ void load_raw(const Args& a, int row, bool ok, Raw& r) {
+        r.beta = T(0); r.mm = T(0); r.sv = T(0); r.ul = T(0);
+        if (ok) { r.beta = a.std_beta[row]; r.mm = a.mu_mult[row]; r.sv = a.sqrt_half_var_tau[row]; r.ul = a.u_logs[row]; }
+    }
+    static __device__ __forceinline__ void derive(const Args& a, const Raw& r, Lane& L) {
+        L.c0 = mul_t(r.mm, r.beta);          // mu = fma(mu_mult, beta, -mu_mult*q)   (:401)  with q = dq * X
+        L.c1 = -mul_t(r.mm, a.dq);
+        L.sv = r.sv; L.ul = r.ul;
     }
     // X: F_j + B_j in LD-code units; eo: eta_j before the update
     static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
         const T mu = fma_t(L.c1, X, L.c0);
-        const T uu = L.sv * mu;                                   // :404
+        const T uu = mul_t(L.sv, mu);                             // :404
         const T g = sigmoid_t(fma_t(uu, uu, L.ul));               // :405
         d = fma_t(g, mu, -eo);                                    // :408
         skip = abs_t(d) < eps;                                    // :410-413
-        en = skip ? eo : eo + d;                                  // :431
-        if (skip) d = T(0);
+        en = skip ? eo : add_t(eo, d);                            // :431
         o.mu = mu; o.g = g;
     }
     static __device__ __forceinline__ void store(const Args& a, int row, bool skip, const Out& o) {
@@ -114,48 +130,54 @@ struct MixModel {
         const T* std_beta; const T* u_logs; const T* sqrt_half_var_tau; const T* mu_mult; const T* log_null_pi;
         T* var_gamma; T* var_mu; T dq; int K;
     };
-    struct Lane { T beta, lnp; T mm[KMAX], sv[KMAX], ul[KMAX]; int K; T dq; };
+    static constexpr bool kHeavy = (KMAX > 4);       // register-hungry: always one CTA per SM
+    struct Raw { T beta, lnp; T mm[KMAX], sv[KMAX], ul[KMAX]; };
+    struct Lane { T beta, lnp, dq; T mm[KMAX], sv[KMAX], ul[KMAX]; int K; };
     struct Out { T mu[KMAX], g[KMAX]; };
-    static __device__ __forceinline__ void load(const Args& a, int row, bool ok, Lane& L) {
-        L.K = a.K; L.dq = a.dq;
-        L.beta = ok ? a.std_beta[row] : T(0);
-        L.lnp = ok ? a.log_null_pi[row] : T(0);
+    static __device__ __forceinline__ void load_raw(const Args& a, int row, bool ok, Raw& r) {
+        r.beta = ok ? a.std_beta[row] : T(0);
+        r.lnp = ok ? a.log_null_pi[row] : T(0);
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const bool v = ok && k < a.K;
             const size_t m = (size_t)row * a.K + k;
-            L.mm[k] = v ? a.mu_mult[m] : T(0);
-            L.sv[k] = v ? a.sqrt_half_var_tau[m] : T(0);
-            L.ul[k] = v ? a.u_logs[m] : T(0);
+            r.mm[k] = v ? a.mu_mult[m] : T(0);
+            r.sv[k] = v ? a.sqrt_half_var_tau[m] : T(0);
+            r.ul[k] = v ? a.u_logs[m] : T(0);
         }
+    }
+    static __device__ __forceinline__ void derive(const Args& a, const Raw& r, Lane& L) {
+        L.beta = r.beta; L.lnp = r.lnp; L.dq = a.dq; L.K = a.K;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) { L.mm[k] = r.mm[k]; L.sv[k] = r.sv[k]; L.ul[k] = r.ul[k]; }
     }
     static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
         (void)eps;
-        const T r = L.beta - L.dq * X;                            // :505
+        const T r = fma_t(-L.dq, X, L.beta);                      // :505
         T u[KMAX];
         T mx = L.lnp;                                             // :515, c_max :58-71
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
-            o.mu[k] = L.mm[k] * r;                                // :509
-            const T t = L.sv[k] * o.mu[k];                        // :510
+            o.mu[k] = mul_t(L.mm[k], r);                          // :509
+            const T t = mul_t(L.sv[k], o.mu[k]);                  // :510
             u[k] = fma_t(t, t, L.ul[k]);                          // :511
             if (k < L.K) mx = u[k] > mx ? u[k] : mx;
         }
-        T sum = exp_t(L.lnp - mx);                                // softmax :222-241
+        T sum = expneg_t(mx - L.lnp);                             // softmax :222-241 (max-shifted)
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
-            u[k] = (k < L.K) ? exp_t(u[k] - mx) : T(0);
-            sum += u[k];
+            u[k] = (k < L.K) ? expneg_t(mx - u[k]) : T(0);
+            sum = add_t(sum, u[k]);
         }
-        const T inv = rcp_t(sum);
+        const T inv = fast_rcp_t(sum);
         d = -eo;                                                  // :519
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
-            o.g[k] = u[k] * inv;
+            o.g[k] = mul_t(u[k], inv);
             d = fma_t(o.g[k], o.mu[k], d);                        // :523
         }
         skip = false;                                             // no skip branch in the mixture sweep
-        en = eo + d;                                              // :536
+        en = add_t(eo, d);                                        // :536
     }
     static __device__ __forceinline__ void store(const Args& a, int row, bool skip, const Out& o) {
         (void)skip;
@@ -172,12 +194,23 @@ template <> __device__ __forceinline__ double eps_of<double>() { return 1e-8; } 
 template <typename T>
 struct StateArgs { T* eta; T* q; T* eta_diff; };
 
+template <typename T> __device__ __forceinline__ void load_state_vec(const T* src, T* dst, int n16) {
+    const uint4* sp = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (e < n16) {
+            const uint4 t = sp[e];
+            memcpy(reinterpret_cast<unsigned char*>(dst) + 16 * e, &t, 16);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the sweep kernel
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename U, typename Model, int MINB>
 __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const SweepPlan p, const typename Model::Args ma,
-                                                                 const StateArgs<T> sa) {
+                                                                       const StateArgs<T> sa) {
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int ES = (int)sizeof(U);
     constexpr int TPV = EPV * (int)sizeof(T) / 16;       // 16-byte chunks of state per LD vector
@@ -189,11 +222,11 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
     int4* panelmeta = reinterpret_cast<int4*>(smem + p.L.panelmeta);  // [NST] {P, vmin, vmax, first local row}
     T* partial = reinterpret_cast<T*>(smem + p.L.partial);            // [NBW][RR]
     T* alpha = reinterpret_cast<T*>(smem + p.L.alpha);                // [RR]  eta_new of finished rows
+    T* wwin = reinterpret_cast<T*>(smem + p.L.wwin);                  // [RR][WW] R[j][j+1+k] for k < cut_j-j-1, else 0
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
     uint64_t* empty = full + NST_MAX;
-    uint32_t* a_prog = reinterpret_cast<uint32_t*>(smem + p.L.counters);   // [NBW] panels whose A this warp finished
-    uint32_t* c_prog = a_prog + NBW;                                        // [NBW] panels whose C this warp finished
-    uint32_t* rows_done = a_prog + 2 * NBW;                                 // rows the chain warp has retired
+    uint64_t* cdone = full + 2 * NST_MAX;
+    uint32_t* prog = reinterpret_cast<uint32_t*>(smem + p.L.counters);      // a_prog[NBW] | c_prog[NBW]
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int blk = p.blk_order[blockIdx.x];
@@ -209,14 +242,13 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
         f_s[i] = T(0);
     }
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NBW); }
-        for (int w = 0; w < NBW; ++w) { a_prog[w] = 0; c_prog[w] = 0; }
-        *rows_done = 0;
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NBW); mbar_init(&cdone[s], 1); }
+        for (int w = 0; w < 2 * NBW; ++w) prog[w] = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
-    if (warp == 1) {
+    if (warp == NBW) {
         // =============================== producer ===========================================
         const unsigned char* gsrc = p.packed;
         if (lane == 0) {
@@ -226,8 +258,8 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
                 if (o1 > o0) tma_prefetch_l2(gsrc + o0 * ES, (uint32_t)((o1 - o0) * ES));
             }
         }
+        int s = 0, k = 0;
         for (int v = 0; v < NP; ++v) {
-            const int s = v % NST, k = v / NST;
             const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
             const int P = re - rs;
             const int64_t obase = p.prow[rs];
@@ -235,7 +267,9 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
             int64_t o0 = 0, o1 = 0;
             int c = 0;
             if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
+            trace_ev(p, lane, 9, 0, v);
             if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+            trace_ev(p, lane, 9, 1, v);
             int vs = 0x7fffffff, ve = 0;
             if (lane < P) {
                 const int nv = (int)(o1 - o0) / EPV;
@@ -261,22 +295,32 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
                 } else {
                     mbar_arrive(&full[s]);
                 }
+                trace_ev(p, lane, 9, 2, v);
                 const int vp = v + NST + p.l2_ahead;
                 if (vp < NP) {
                     const int64_t q0 = p.prow[p.panel_row[pan0 + vp]], q1 = p.prow[p.panel_row[pan0 + vp + 1]];
                     if (q1 > q0) tma_prefetch_l2(gsrc + q0 * ES, (uint32_t)((q1 - q0) * ES));
                 }
             }
+            if (++s == NST) { s = 0; ++k; }
         }
-    } else if (warp == 0) {
+    } else if (warp == NBW + 1) {
         // =============================== chain ==============================================
         const T eps = eps_of<T>();
         const T dq = ma.dq;
         typename Model::Lane L;
-        Model::load(ma, r0 + lane, lane < B, L);
+        typename Model::Raw pend;                       // parameters of the lane's next column, in flight
+        bool has_pend = false;
+        T eo_pend = T(0);
+        {
+            typename Model::Raw r;
+            Model::load_raw(ma, r0 + lane, lane < B, r);
+            Model::derive(ma, r, L);
+            Model::load_raw(ma, r0 + lane, false, pend);
+        }
         T eo = (lane < B) ? eta_s[lane] : T(0);
         T X0 = T(0), X1 = T(0);
-        int j0 = 0;
+        int j0 = 0, s = 0;
         int rs_next = p.panel_row[pan0 + 1] - r0;
         int need_c = p.panel_need[pan0];
         for (int u = 0; u < NP; ++u) {
@@ -286,10 +330,11 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
             const int rel = (lane - base) & 31;
             const int need_c_cur = need_c;
             if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
-            wait_all_ge(a_prog, (uint32_t)(u + 1), lane);
-            wait_all_ge(c_prog, (uint32_t)need_c_cur, lane);
+            trace_ev(p, lane, 8, 0, u);
+            wait_progress(prog, (uint32_t)(u + 1), (uint32_t)need_c_cur, lane);
+            trace_ev(p, lane, 8, 1, u);
 
-            // fold what the bulk warps prepared for this batch's 16 columns
+            // fold what the bulk warps prepared for this panel's columns
             T bsum = T(0);
             if (rel < nrows) {
                 const int cl = j0 + rel;
@@ -297,163 +342,212 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
                 for (int w = 0; w < NBW; ++w) bsum += partial[w * RR + (cl & (RR - 1))];
                 X0 += f_s[cl] + bsum;
             }
-            typename Model::Out o_out;
-            T o_d = T(0), o_en = T(0), o_F = T(0);
-            bool o_skip = true;
+            T Xown = T(0);
 #pragma unroll
-            for (int h = 0; h < BATCH; h += 8) {
-                T w0[8], w1[8];
+            for (int h = 0; h < PMAX; h += 8) {
+                if (h < nrows) {
+                    T w0[8], w1[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int jl = j0 + h + i;                 // block-local row of this step
-                    w0[i] = T(0); w1[i] = T(0);
-                    if (h + i < nrows) {
-                        const int4 m = rowmeta[jl & (RR - 1)];
-                        const int cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
-                        const int c0 = j0 + rel + ((rel <= h + i) ? 32 : 0);
-                        const int c1 = c0 + 32;
-                        if (c0 < cut && c0 / EPV >= m.y && c0 / EPV < m.z) w0[i] = ld_elem<T, U>(smem + m.x + c0 * ES);
-                        if (c1 < cut && c1 / EPV >= m.y && c1 / EPV < m.z) w1[i] = ld_elem<T, U>(smem + m.x + c1 * ES);
+                    for (int i = 0; i < 8; ++i) {
+                        const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
+                        const T* wr = wwin + ((j0 + h + i) & (RR - 1)) * WW;
+                        w0[i] = (h + i < nrows) ? wr[k0] : T(0);
+                        w1[i] = (h + i < nrows && k0 + 32 < WW) ? wr[k0 + 32] : T(0);
                     }
-                }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (h + i < nrows) {
-                        T en, d;
-                        bool skip;
-                        typename Model::Out o;
-                        Model::step(L, X0, eo, eps, en, d, skip, o);
-                        const bool mine = (rel == h + i);
-                        if (mine) { o_out = o; o_d = d; o_en = en; o_F = X0 - bsum; o_skip = skip; }
-                        const T a = shfl_t(en, (base + h + i) & 31);
-                        if (mine) { X0 = X1; X1 = T(0); }
-                        X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
-                        X1 = fma_t(w1[i], a, X1);
+                    for (int i = 0; i < 8; ++i) {
+                        if (h + i < nrows) {
+                            T en, d;
+                            bool skip;
+                            typename Model::Out o;
+                            Model::step(L, X0, eo, eps, en, d, skip, o);
+                            const bool mine = (rel == h + i);
+                            Xown = mine ? X0 : Xown;
+                            const T a = shfl_t(en, (base + h + i) & 31);
+                            X0 = mine ? X1 : X0;
+                            X1 = mine ? T(0) : X1;
+                            X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
+                            X1 = fma_t(w1[i], a, X1);
+                        }
                     }
                 }
             }
-            // batch epilogue: outputs of the 16 rows, eta_new for the bulk axpy, parameters of the lanes' next columns
+            trace_ev(p, lane, 8, 2, u);
+            // panel epilogue: outputs of the rows (re-evaluated from the saved X: same bits as on the chain),
+            // eta_new for the bulk axpy, parameters of the lanes' next columns
             if (rel < nrows) {
+                T en, d;
+                bool skip;
+                typename Model::Out o;
+                Model::step(L, Xown, eo, eps, en, d, skip, o);
                 const int cl = j0 + rel;
                 const int row = r0 + cl;
-                Model::store(ma, row, o_skip, o_out);
-                if (!o_skip) sa.eta[row] = o_en;                                   // :431
-                sa.eta_diff[row] = o_d;                                            // :413 / :418
-                sa.q[row] = dq * o_F;                                              // forward part of q (see header)
-                alpha[cl & (RR - 1)] = o_en;
+                Model::store(ma, row, skip, o);
+                if (!skip) sa.eta[row] = en;                                       // :431
+                sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
+                sa.q[row] = dq * (Xown - bsum);                                    // forward part of q (see header)
+                alpha[cl & (RR - 1)] = en;
             }
             __syncwarp();
-            if (lane == 0) st_release(rows_done, (uint32_t)(j0 + nrows));
+            if (lane == 0) mbar_arrive(&cdone[s]);
+            trace_ev(p, lane, 8, 3, u);
+            if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; has_pend = false; }
             if (rel < nrows) {
                 const int cn = j0 + rel + 32;
-                Model::load(ma, r0 + cn, cn < B, L);
-                eo = (cn < B) ? eta_s[cn] : T(0);
+                Model::load_raw(ma, r0 + cn, cn < B, pend);
+                eo_pend = (cn < B) ? eta_s[cn] : T(0);
+                has_pend = true;
             }
             j0 += nrows;
+            if (++s == NST) s = 0;
         }
     } else {
         // =============================== bulk ===============================================
-        const int wb = warp - 2;
+        const int wb = warp;
         const int tb = wb * WARP + lane;
-        int cnext = 0;                                     // next panel whose axpy (C) this warp has to do
+        int cnext = 0, cs = 0, ck = 0;                     // next panel whose axpy (C) this warp has to do
 
-        auto do_C = [&](int v) {
-            const int sc = v % NST;
-            const int4 pm = panelmeta[sc];
+        auto do_C = [&]() {
+            trace_ev(p, lane, wb, 4, cnext);
+            const int4 pm = panelmeta[cs];
             const int Pc = pm.x, vmaxc = pm.z, jl0 = pm.w;
             const int first = (jl0 + WIN + EPV - 1) / EPV;
-            int vv = first + (((tb - first) % NBT) + NBT) % NBT;       // static ownership: vv == tb (mod NBT)
+            const int last_cut = (jl0 + Pc - 1 + WIN + EPV - 1) / EPV;     // cut vector of the panel's last row
+            int vv = first + (((tb - first) % NBT) + NBT) % NBT;           // static ownership: vv == tb (mod NBT)
             for (; vv < vmaxc; vv += NBT) {
                 T fs[EPV];
-                uint4* fp = reinterpret_cast<uint4*>(f_s + (size_t)vv * EPV);
+                T* fp = f_s + (size_t)vv * EPV;
+                load_state_vec(fp, fs, TPV);
+                for (int rg = 0; rg < Pc; rg += 4) {
+                    const int nv = min(4, Pc - rg);
+                    int mx[4], my[4], mz[4];
+                    T al[4];
+                    int lo_all = last_cut, hi_all = 0x7fffffff;
 #pragma unroll
-                for (int e = 0; e < TPV; ++e) {
-                    const uint4 t = fp[e];
-                    memcpy(reinterpret_cast<unsigned char*>(fs) + 16 * e, &t, 16);
-                }
-                for (int rg = 0; rg < Pc; rg += 8) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (rg + r < Pc) {
+                    for (int r = 0; r < 4; ++r) {
+                        mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
+                        if (r < nv) {
                             const int jl = jl0 + rg + r;
                             const int4 m = rowmeta[jl & (RR - 1)];
-                            const int lo = max(m.y, (jl + WIN + EPV - 1) / EPV);
-                            if (vv >= lo && vv < m.z) {
-                                const uint4 c = *reinterpret_cast<const uint4*>(smem + m.x + vv * 16);
-                                VecOps<T, U>::axpy(c, alpha[jl & (RR - 1)], fs);
+                            mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
+                            al[r] = alpha[jl & (RR - 1)];
+                            lo_all = max(lo_all, my[r]); hi_all = min(hi_all, mz[r]);
+                        }
+                    }
+                    if (vv >= lo_all && vv < hi_all) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < nv) {
+                                const uint4 c = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
+                                VecOps<T, U>::axpy(c, al[r], fs);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (vv >= my[r] && vv < mz[r]) {
+                                const uint4 c = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
+                                VecOps<T, U>::axpy(c, al[r], fs);
                             }
                         }
                     }
                 }
+                uint4* fq = reinterpret_cast<uint4*>(fp);
 #pragma unroll
                 for (int e = 0; e < TPV; ++e) {
                     uint4 t;
                     memcpy(&t, reinterpret_cast<unsigned char*>(fs) + 16 * e, 16);
-                    fp[e] = t;
+                    fq[e] = t;
                 }
             }
             __syncwarp();
             if (lane == 0) {
-                st_release(&c_prog[wb], (uint32_t)(v + 1));
-                mbar_arrive(&empty[sc]);
+                st_release(&prog[NBW + wb], (uint32_t)(cnext + 1));
+                mbar_arrive(&empty[cs]);
             }
+            trace_ev(p, lane, wb, 5, cnext);
+            ++cnext;
+            if (++cs == NST) { cs = 0; ++ck; }
         };
 
+        int s = 0, k = 0;
         for (int u = 0; u < NP; ++u) {
-            const int s = u % NST;
             // the stage of panel u is only re-filled after C(u - NST): do the overdue axpys first (blocking)
             while (cnext <= u - NST) {
-                wait_ge(rows_done, (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0));
-                do_C(cnext++);
+                mbar_wait(&cdone[cs], ck & 1);
+                do_C();
             }
-            mbar_wait(&full[s], (u / NST) & 1);
-            {
-                // ---- A(u): backward dots of the rows of panel u --------------------------------
-                const int4 pm = panelmeta[s];
-                const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
-                for (int rg = 0; rg < P; rg += 8) {
-                    typename Pk<T>::acc_t acc2[8];
-                    int mx[8], my[8], mz[8];
+            trace_ev(p, lane, wb, 0, u);
+            mbar_wait(&full[s], k & 1);
+            trace_ev(p, lane, wb, 1, u);
+            const int4 pm = panelmeta[s];
+            const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
+            // ---- window coefficients of the panel's rows (row r of the panel -> bulk warp r % NBW) ----
+            for (int r = wb; r < P; r += NBW) {
+                const int jl = jl0 + r;
+                const int4 m = rowmeta[jl & (RR - 1)];
+                const int cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        acc2[r] = Pk<T>::zero();
-                        mx[r] = 0; my[r] = 0; mz[r] = 0;
-                        if (rg + r < P) {
-                            const int4 m = rowmeta[(jl0 + rg + r) & (RR - 1)];
-                            mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
-                        }
+                for (int kk = lane; kk < WW; kk += WARP) {
+                    const int col = jl + 1 + kk;
+                    T v = T(0);
+                    if (col < cut && col / EPV >= m.y && col / EPV < m.z) v = ld_elem<T, U>(smem + m.x + col * ES);
+                    wwin[(jl & (RR - 1)) * WW + kk] = v;
+                }
+            }
+            // ---- A(u): backward dots of the rows of panel u ----------------------------------
+            for (int rg = 0; rg < P; rg += 4) {
+                const int nv = min(4, P - rg);
+                typename Pk<T>::acc_t acc2[4];
+                int mx[4], my[4], mz[4];
+                int lo_all = 0, hi_all = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc2[r] = Pk<T>::zero();
+                    mx[r] = 0; my[r] = 0; mz[r] = 0;
+                    if (r < nv) {
+                        const int4 m = rowmeta[(jl0 + rg + r) & (RR - 1)];
+                        mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                        lo_all = max(lo_all, m.y); hi_all = min(hi_all, m.z);
                     }
-                    for (int v = vmin + tb; v < vmax; v += NBT) {
-                        T es[EPV];
-                        const uint4* ep = reinterpret_cast<const uint4*>(eta_s + (size_t)v * EPV);
+                }
+                for (int v = vmin + tb; v < vmax; v += NBT) {
+                    T es[EPV];
+                    load_state_vec(eta_s + (size_t)v * EPV, es, TPV);
+                    if (v >= lo_all && v < hi_all) {
 #pragma unroll
-                        for (int e = 0; e < TPV; ++e) {
-                            const uint4 t = ep[e];
-                            memcpy(reinterpret_cast<unsigned char*>(es) + 16 * e, &t, 16);
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < nv) {
+                                const uint4 c = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+                                VecOps<T, U>::dot(c, es, acc2[r]);
+                            }
                         }
+                    } else {
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) {
+                        for (int r = 0; r < 4; ++r) {
                             if (v >= my[r] && v < mz[r]) {
                                 const uint4 c = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
                                 VecOps<T, U>::dot(c, es, acc2[r]);
                             }
                         }
                     }
-                    T acc[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) acc[r] = Pk<T>::sum(acc2[r]);
-                    const int rr = warp_reduce8(acc, lane);
-                    if ((lane & 3) == 0 && rg + rr < P) partial[wb * RR + ((jl0 + rg + rr) & (RR - 1))] = acc[0];
                 }
+                T acc[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = Pk<T>::sum(acc2[r]);
+                const int rr = warp_reduce4(acc, lane);
+                if ((lane & 7) == 0 && rr < nv) partial[wb * RR + ((jl0 + rg + rr) & (RR - 1))] = acc[0];
             }
             __syncwarp();
-            if (lane == 0) st_release(&a_prog[wb], (uint32_t)(u + 1));
+            if (lane == 0) st_release(&prog[wb], (uint32_t)(u + 1));
+            trace_ev(p, lane, wb, 2, u);
             // opportunistic axpys: every panel the chain has already finished
-            while (cnext <= u && ld_acquire(rows_done) >= (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0)) do_C(cnext++);
+            while (cnext <= u && mbar_test(&cdone[cs], ck & 1)) do_C();
+            if (++s == NST) { s = 0; ++k; }
         }
         while (cnext < NP) {
-            wait_ge(rows_done, (uint32_t)(p.panel_row[pan0 + cnext + 1] - r0));
-            do_C(cnext++);
+            mbar_wait(&cdone[cs], ck & 1);
+            do_C();
         }
     }
 }
