@@ -11,7 +11,8 @@ extern "C" int viprs_b200_ld_info(const viprs_b200_ld_t* h, viprs_b200_ld_info_t
     info->M = h->M; info->ld_dtype = h->ld_dtype; info->n_blocks = h->n_blocks; info->max_block = h->max_block;
     info->n_panels = h->n_panels; info->stage_bytes = h->stage_bytes; info->nnz = h->nnz;
     info->packed_elems = h->packed_elems;
-    const vb::RingGeometry g = vb::ring_geometry(h, 4);
+    vb::RingGeometry g = vb::fast_ring_geometry(h);
+    if (g.nst == 0) g = vb::ring_geometry(h, 4);
     info->smem_bytes = g.smem_bytes;
     info->ring_stages = g.nst;
     info->ctas_per_sm = g.ctas_per_sm;

@@ -104,13 +104,14 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t target) {
     }
 }
 
-// All 2*NBW per-warp progress counters reached their targets: prog[0..NBW) >= ta, prog[NBW..2NBW) >= tc.
-// Called by a full warp; lane l < 2*NBW polls counter l.
+// All per-warp progress counters reached their targets: prog[0..NA) >= ta, prog[NA..NA+NC) >= tc.
+// Called by a full warp; lane l < NA+NC polls counter l.
+template <int NA, int NC>
 __device__ __forceinline__ void wait_progress(const uint32_t* prog, uint32_t ta, uint32_t tc, int lane) {
     uint32_t spins = 0;
-    const uint32_t target = lane < NBW ? ta : tc;
+    const uint32_t target = lane < NA ? ta : tc;
     for (;;) {
-        const bool ok = (lane >= 2 * NBW) || (ld_acquire(prog + lane) >= target);
+        const bool ok = (lane >= NA + NC) || (ld_acquire(prog + lane) >= target);
         if (__all_sync(0xffffffffu, ok)) break;
         if (++spins > kSpinLimit) __trap();
     }

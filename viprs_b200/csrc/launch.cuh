@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "ld.h"
 #include "sweep.cuh"
+#include "sweep_fast.cuh"
 
 namespace vb {
 
@@ -18,7 +19,6 @@ static int env_int(const char* name, int dflt) {
 
 static int make_plan(const viprs_b200_ld* ld, int tsize, SweepPlan& p, RingGeometry& g) {
     g = ring_geometry(ld, tsize);
-    if (g.nst == 0) return VIPRS_B200_EBLOCK_TOO_LARGE;
     p.packed = reinterpret_cast<const unsigned char*>(ld->d_packed);
     p.prow = ld->d_prow; p.pcs = ld->d_pcs; p.blk_row = ld->d_blk_row; p.blk_panel = ld->d_blk_panel;
     p.panel_row = ld->d_panel_row; p.blk_order = ld->d_blk_order; p.panel_need = ld->d_panel_need;
@@ -26,7 +26,29 @@ static int make_plan(const viprs_b200_ld* ld, int tsize, SweepPlan& p, RingGeome
     p.l2_ahead = env_int("VIPRS_B200_L2_AHEAD", 8);
     p.trace = nullptr;
     p.L = make_layout(p.bpad, tsize, ld->stage_bytes, g.nst);
-    return VIPRS_B200_OK;
+    return g.nst == 0 ? VIPRS_B200_EBLOCK_TOO_LARGE : VIPRS_B200_OK;
+}
+
+// run `launch(plan)`; with VIPRS_B200_TRACE=<file> (debug only) also dump the timeline of CTA 0
+template <typename F>
+static int launch_traced(const SweepPlan& p, cudaStream_t st, F&& launch) {
+    const char* trace_path = getenv("VIPRS_B200_TRACE");
+    if (trace_path) {
+        SweepPlan pt = p;
+        const size_t nb = (size_t)kTraceSlots * sizeof(unsigned long long);
+        if (cudaMalloc(&pt.trace, nb) != cudaSuccess) return VIPRS_B200_ENOMEM;
+        cudaMemsetAsync(pt.trace, 0, nb, st);
+        launch(pt);
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(kTraceSlots);
+        cudaMemcpy(h.data(), pt.trace, nb, cudaMemcpyDeviceToHost);
+        cudaFree(pt.trace);
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 1, nb, f); fclose(f); }
+    } else {
+        launch(p);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
 }
 
 template <typename T, typename U, typename Model, int MINB>
@@ -35,30 +57,45 @@ static int launch_one(const viprs_b200_ld* ld, const SweepPlan& p, const RingGeo
     auto kern = sweep_kernel<T, U, Model, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    const char* trace_path = getenv("VIPRS_B200_TRACE");      // debug only: timeline of CTA 0 of every launch
-    if (trace_path) {
-        SweepPlan pt = p;
-        const size_t nb = (size_t)kTraceSlots * sizeof(unsigned long long);
-        if (cudaMalloc(&pt.trace, nb) != cudaSuccess) return VIPRS_B200_ENOMEM;
-        cudaMemsetAsync(pt.trace, 0, nb, st);
-        kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(pt, ma, sa);
-        cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(kTraceSlots);
-        cudaMemcpy(h.data(), pt.trace, nb, cudaMemcpyDeviceToHost);
-        cudaFree(pt.trace);
-        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 1, nb, f); fclose(f); }
-        e = cudaGetLastError();
-        return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
-    }
-    kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(p, ma, sa);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+    return launch_traced(p, st, [&](const SweepPlan& pp) {
+        kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(pp, ma, sa);
+    });
+}
+
+// register-resident kernel (float32 state, LD blocks <= 4096 SNPs, two CTAs per SM)
+template <typename U, typename Model, int NLIMB>
+static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
+                           const StateArgs<float>& sa, cudaStream_t st) {
+    const RingGeometry g = fast_ring_geometry(ld);
+    const FastLayout FL = make_fast_layout(ld->stage_bytes, g.nst);
+    p.nst = g.nst;
+    p.L.stages = FL.stages;
+    auto kern = sweep_fast_kernel<U, Model, NLIMB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
+    if (e != cudaSuccess) return (int)e;
+    return launch_traced(p, st, [&](const SweepPlan& pp) {
+        kern<<<ld->n_blocks, (NBW + 2) * WARP, FL.total, st>>>(pp, FL, ma, sa);
+    });
+}
+
+template <typename T, typename U, typename Model>
+static bool fast_path_ok(const viprs_b200_ld* ld) {
+    if constexpr (sizeof(T) != 4 || Model::kHeavy || sizeof(U) == 8) return false;
+    return ld->max_block <= FAST_MAX_BLOCK && fast_ring_geometry(ld).nst >= 3 && env_int("VIPRS_B200_FORCE_GENERIC", 0) == 0;
 }
 
 template <typename T, typename U, typename Model>
 static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma, const StateArgs<T>& sa, cudaStream_t st) {
     SweepPlan p;
     RingGeometry g;
+    if constexpr (sizeof(T) == 4 && !Model::kHeavy && sizeof(U) != 8) {
+        if (fast_path_ok<T, U, Model>(ld)) {
+            make_plan(ld, (int)sizeof(T), p, g);        // ring fields are overridden by the fast launcher
+            if (std::is_same<U, int8_t>::value && env_int("VIPRS_B200_LIMBS", 4) == 3)
+                return launch_fast_one<U, Model, 3>(ld, p, ma, sa, st);
+            return launch_fast_one<U, Model, 4>(ld, p, ma, sa, st);
+        }
+    }
     int rc = make_plan(ld, (int)sizeof(T), p, g);
     if (rc) return rc;
     if constexpr (!Model::kHeavy) {

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "ld.h"
 #include "sweep.cuh"
+#include "sweep_fast.cuh"
 
 namespace vb {
 
@@ -113,6 +114,18 @@ RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize) {
     return g;
 }
 
+RingGeometry fast_ring_geometry(const viprs_b200_ld* ld) {
+    RingGeometry g{0, 0, 0};
+    if (ld->max_block > FAST_MAX_BLOCK) return g;
+    const int st = (int)make_fast_layout(0, 0).total;
+    int nst = (kSmemTwoPerSM - st) / ld->stage_bytes;
+    if (nst > NST_MAX) nst = NST_MAX;
+    if (nst < 3) return g;
+    g.nst = nst; g.ctas_per_sm = 2;
+    g.smem_bytes = (int)make_fast_layout(ld->stage_bytes, nst).total;
+    return g;
+}
+
 // pick the TMA stage size: four stages next to the float32 block state if two CTAs can share an SM,
 // otherwise four stages of a single CTA per SM; never smaller than the longest packed row.
 static int choose_stage_bytes(int max_block, int max_row_bytes, int smem_optin, int requested) {
@@ -122,7 +135,7 @@ static int choose_stage_bytes(int max_block, int max_row_bytes, int smem_optin, 
     if (requested > 0) {
         sb = requested;
     } else {
-        const int st = state_bytes(max_block, 4);
+        const int st = max_block <= FAST_MAX_BLOCK ? (int)make_fast_layout(0, 0).total : state_bytes(max_block, 4);
         sb = (kSmemTwoPerSM - st) / 4;
         if (sb < max_row_bytes || sb < 2048) sb = (smem_optin - st) / 4;
         if (sb > 48 * 1024) sb = 48 * 1024;
@@ -222,7 +235,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         h->h_blk_row = blk_row;
         stage_bytes = vb::choose_stage_bytes(max_block, max_row_bytes, h->smem_optin, stage_bytes);
         h->stage_bytes = stage_bytes;
-        if (vb::ring_geometry(h, 4).nst == 0) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
+        if (vb::ring_geometry(h, 4).nst == 0 && vb::fast_ring_geometry(h).nst == 0) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
 
         // ---- row panels (one TMA bulk copy each) and the chain warp's axpy prerequisites --------
         std::vector<int32_t> blk_panel(nb + 1), panel_row, panel_need;

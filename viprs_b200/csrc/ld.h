@@ -40,4 +40,6 @@ constexpr int kSmemTwoPerSM = 113 * 1024;
 struct RingGeometry { int nst; int smem_bytes; int ctas_per_sm; };
 // ring depth / dynamic shared memory of the sweep for a state type of `tsize` bytes; nst == 0: does not fit
 RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize);
+// same for the register-resident kernel (float32 state, blocks <= 4096 SNPs); nst == 0: not applicable
+RingGeometry fast_ring_geometry(const viprs_b200_ld* ld);
 }  // namespace vb

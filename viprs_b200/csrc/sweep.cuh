@@ -206,27 +206,237 @@ template <typename T> __device__ __forceinline__ void load_state_vec(const T* sr
 }
 
 // ---------------------------------------------------------------------------------------------
-// the sweep kernel
+// shared-memory views and the two roles both kernels share (producer, chain)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct SmemView {
+    unsigned char* base;
+    int4* rowmeta;      // [RR] {byte offset of column 0 of the row, vs, ve, -}
+    int4* panelmeta;    // [NST] {P, vmin, vmax, first local row}
+    T* partial;         // [n_A_warps][RR] backward-dot partials
+    T* alpha;           // [RR] eta_new of finished rows
+    T* wwin;            // [RR][WW] R[j][j+1+k] for k < cut_j-j-1, else 0
+    uint64_t* full;     // [NST] TMA landed
+    uint64_t* empty;    // [NST] every C warp is done with the stage
+    uint64_t* cdone;    // [NST] chain finished the panel
+    uint32_t* prog;     // a_prog[NA] | c_prog[NC]
+    const T* fsrc;      // forward accumulator as the chain reads it: fsrc[col & fmask]
+    int fmask;
+};
+
+template <typename U>
+__device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char* smem, int4* rowmeta, int4* panelmeta,
+                                              uint64_t* full, uint64_t* empty, int r0, int pan0, int NP, int lane) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+    const int NST = p.nst;
+    const unsigned char* gsrc = p.packed;
+    if (lane == 0) {
+        const int npf = min(NP, NST + p.l2_ahead);
+        for (int v = NST; v < npf; ++v) {
+            const int64_t o0 = p.prow[p.panel_row[pan0 + v]], o1 = p.prow[p.panel_row[pan0 + v + 1]];
+            if (o1 > o0) tma_prefetch_l2(gsrc + o0 * ES, (uint32_t)((o1 - o0) * ES));
+        }
+    }
+    int s = 0, k = 0;
+    for (int v = 0; v < NP; ++v) {
+        const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
+        const int P = re - rs;
+        const int64_t obase = p.prow[rs];
+        const int64_t oend = p.prow[re];
+        int64_t o0 = 0, o1 = 0;
+        int c = 0;
+        if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
+        trace_ev(p, lane, 9, 0, v);
+        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+        trace_ev(p, lane, 9, 1, v);
+        int vs = 0x7fffffff, ve = 0;
+        if (lane < P) {
+            const int nv = (int)(o1 - o0) / EPV;
+            const int vs_r = c / EPV;
+            int4 m;
+            m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
+            m.y = vs_r; m.z = vs_r + nv; m.w = 0;
+            rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
+            if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vs = min(vs, __shfl_xor_sync(0xffffffffu, vs, o));
+            ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
+        }
+        const uint32_t bytes = (uint32_t)((oend - obase) * ES);
+        if (lane == 0) panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
+        __syncwarp();
+        if (lane == 0) {
+            if (bytes > 0) {
+                mbar_arrive_expect_tx(&full[s], bytes);
+                tma_load_1d(smem + p.L.stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
+            } else {
+                mbar_arrive(&full[s]);
+            }
+            trace_ev(p, lane, 9, 2, v);
+            const int vp = v + NST + p.l2_ahead;
+            if (vp < NP) {
+                const int64_t q0 = p.prow[p.panel_row[pan0 + vp]], q1 = p.prow[p.panel_row[pan0 + vp + 1]];
+                if (q1 > q0) tma_prefetch_l2(gsrc + q0 * ES, (uint32_t)((q1 - q0) * ES));
+            }
+        }
+        if (++s == NST) { s = 0; ++k; }
+    }
+}
+
+// NA / NC: number of bulk warps that publish a_prog / c_prog (and dot partials)
+template <typename T, typename Model, int NA, int NC>
+__device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
+                                           const SmemView<T>& sm, int r0, int B, int pan0, int NP, int lane) {
+    const int NST = p.nst;
+    const T eps = eps_of<T>();
+    const T dq = ma.dq;
+    typename Model::Lane L;
+    typename Model::Raw pend;                       // parameters of the lane's next column, in flight
+    bool has_pend = false;
+    T eo_pend = T(0);
+    {
+        typename Model::Raw r;
+        Model::load_raw(ma, r0 + lane, lane < B, r);
+        Model::derive(ma, r, L);
+        Model::load_raw(ma, r0 + lane, false, pend);
+    }
+    T eo = (lane < B) ? sa.eta[r0 + lane] : T(0);
+    T X0 = T(0), X1 = T(0);
+    int j0 = 0, s = 0;
+    int rs_next = p.panel_row[pan0 + 1] - r0;
+    int need_c = p.panel_need[pan0];
+    for (int u = 0; u < NP; ++u) {
+        // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
+        const int nrows = rs_next - j0;
+        const int base = j0 & 31;
+        const int rel = (lane - base) & 31;
+        const int need_c_cur = need_c;
+        if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
+        trace_ev(p, lane, 8, 0, u);
+        wait_progress<NA, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c_cur, lane);
+        trace_ev(p, lane, 8, 1, u);
+
+        // fold what the bulk warps prepared for this panel's columns
+        T bsum = T(0);
+        if (rel < nrows) {
+            const int cl = j0 + rel;
+#pragma unroll
+            for (int w = 0; w < NA; ++w) bsum += sm.partial[w * RR + (cl & (RR - 1))];
+            X0 += sm.fsrc[cl & sm.fmask] + bsum;
+        }
+        T Xown = T(0);
+#pragma unroll
+        for (int h = 0; h < PMAX; h += 8) {
+            if (h < nrows) {
+                T w0[8], w1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
+                    const T* wr = sm.wwin + ((j0 + h + i) & (RR - 1)) * WW;
+                    w0[i] = (h + i < nrows) ? wr[k0] : T(0);
+                    w1[i] = (h + i < nrows && k0 + 32 < WW) ? wr[k0 + 32] : T(0);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (h + i < nrows) {
+                        T en, d;
+                        bool skip;
+                        typename Model::Out o;
+                        Model::step(L, X0, eo, eps, en, d, skip, o);
+                        const bool mine = (rel == h + i);
+                        Xown = mine ? X0 : Xown;
+                        const T a = shfl_t(en, (base + h + i) & 31);
+                        X0 = mine ? X1 : X0;
+                        X1 = mine ? T(0) : X1;
+                        X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
+                        X1 = fma_t(w1[i], a, X1);
+                    }
+                }
+            }
+        }
+        trace_ev(p, lane, 8, 2, u);
+        // panel epilogue: outputs of the rows (re-evaluated from the saved X: same bits as on the chain),
+        // eta_new for the bulk axpy, parameters of the lanes' next columns
+        if (rel < nrows) {
+            T en, d;
+            bool skip;
+            typename Model::Out o;
+            Model::step(L, Xown, eo, eps, en, d, skip, o);
+            const int cl = j0 + rel;
+            const int row = r0 + cl;
+            Model::store(ma, row, skip, o);
+            if (!skip) sa.eta[row] = en;                                       // :431
+            sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
+            sa.q[row] = dq * (Xown - bsum);                                    // forward part of q (see header)
+            sm.alpha[cl & (RR - 1)] = en;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.cdone[s]);
+        trace_ev(p, lane, 8, 3, u);
+        if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; has_pend = false; }
+        if (rel < nrows) {
+            const int cn = j0 + rel + 32;
+            Model::load_raw(ma, r0 + cn, cn < B, pend);
+            eo_pend = (cn < B) ? sa.eta[r0 + cn] : T(0);                       // not yet rewritten: cn is >= 16 rows ahead
+            has_pend = true;
+        }
+        j0 += nrows;
+        if (++s == NST) s = 0;
+    }
+}
+
+// window coefficients of row jl (block-local) of a landed panel -> wwin ring (one warp per row)
+template <typename T, typename U>
+__device__ __forceinline__ void window_row(unsigned char* smem, const int4* rowmeta, T* wwin, int jl, int lane) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+    const int4 m = rowmeta[jl & (RR - 1)];
+    const int cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
+#pragma unroll
+    for (int kk = lane; kk < WW; kk += WARP) {
+        const int col = jl + 1 + kk;
+        T v = T(0);
+        if (col < cut && col / EPV >= m.y && col / EPV < m.z) v = ld_elem<T, U>(smem + m.x + col * ES);
+        wwin[(jl & (RR - 1)) * WW + kk] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the generic sweep kernel: any state type, any block size that fits; block state in shared memory
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename U, typename Model, int MINB>
 __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const SweepPlan p, const typename Model::Args ma,
                                                                        const StateArgs<T> sa) {
     constexpr int EPV = LdTraits<U>::EPV;
-    constexpr int ES = (int)sizeof(U);
     constexpr int TPV = EPV * (int)sizeof(T) / 16;       // 16-byte chunks of state per LD vector
     extern __shared__ __align__(128) unsigned char smem[];
 
     T* eta_s = reinterpret_cast<T*>(smem + p.L.eta);
     T* f_s = reinterpret_cast<T*>(smem + p.L.f);
-    int4* rowmeta = reinterpret_cast<int4*>(smem + p.L.rowmeta);      // [RR] {byte offset of column 0, vs, ve, -}
-    int4* panelmeta = reinterpret_cast<int4*>(smem + p.L.panelmeta);  // [NST] {P, vmin, vmax, first local row}
-    T* partial = reinterpret_cast<T*>(smem + p.L.partial);            // [NBW][RR]
-    T* alpha = reinterpret_cast<T*>(smem + p.L.alpha);                // [RR]  eta_new of finished rows
-    T* wwin = reinterpret_cast<T*>(smem + p.L.wwin);                  // [RR][WW] R[j][j+1+k] for k < cut_j-j-1, else 0
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
-    uint64_t* empty = full + NST_MAX;
-    uint64_t* cdone = full + 2 * NST_MAX;
-    uint32_t* prog = reinterpret_cast<uint32_t*>(smem + p.L.counters);      // a_prog[NBW] | c_prog[NBW]
+    SmemView<T> sm;
+    sm.base = smem;
+    sm.rowmeta = reinterpret_cast<int4*>(smem + p.L.rowmeta);
+    sm.panelmeta = reinterpret_cast<int4*>(smem + p.L.panelmeta);
+    sm.partial = reinterpret_cast<T*>(smem + p.L.partial);
+    sm.alpha = reinterpret_cast<T*>(smem + p.L.alpha);
+    sm.wwin = reinterpret_cast<T*>(smem + p.L.wwin);
+    sm.full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
+    sm.empty = sm.full + NST_MAX;
+    sm.cdone = sm.full + 2 * NST_MAX;
+    sm.prog = reinterpret_cast<uint32_t*>(smem + p.L.counters);
+    sm.fsrc = f_s;
+    sm.fmask = 0x7fffffff;
+    int4* rowmeta = sm.rowmeta;
+    int4* panelmeta = sm.panelmeta;
+    T* partial = sm.partial;
+    T* alpha = sm.alpha;
+    uint64_t* full = sm.full;
+    uint64_t* empty = sm.empty;
+    uint64_t* cdone = sm.cdone;
+    uint32_t* prog = sm.prog;
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int blk = p.blk_order[blockIdx.x];
@@ -249,158 +459,9 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
     __syncthreads();
 
     if (warp == NBW) {
-        // =============================== producer ===========================================
-        const unsigned char* gsrc = p.packed;
-        if (lane == 0) {
-            const int npf = min(NP, NST + p.l2_ahead);
-            for (int v = NST; v < npf; ++v) {
-                const int64_t o0 = p.prow[p.panel_row[pan0 + v]], o1 = p.prow[p.panel_row[pan0 + v + 1]];
-                if (o1 > o0) tma_prefetch_l2(gsrc + o0 * ES, (uint32_t)((o1 - o0) * ES));
-            }
-        }
-        int s = 0, k = 0;
-        for (int v = 0; v < NP; ++v) {
-            const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
-            const int P = re - rs;
-            const int64_t obase = p.prow[rs];
-            const int64_t oend = p.prow[re];
-            int64_t o0 = 0, o1 = 0;
-            int c = 0;
-            if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
-            trace_ev(p, lane, 9, 0, v);
-            if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-            trace_ev(p, lane, 9, 1, v);
-            int vs = 0x7fffffff, ve = 0;
-            if (lane < P) {
-                const int nv = (int)(o1 - o0) / EPV;
-                const int vs_r = c / EPV;
-                int4 m;
-                m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
-                m.y = vs_r; m.z = vs_r + nv; m.w = 0;
-                rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
-                if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                vs = min(vs, __shfl_xor_sync(0xffffffffu, vs, o));
-                ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
-            }
-            const uint32_t bytes = (uint32_t)((oend - obase) * ES);
-            if (lane == 0) panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
-            __syncwarp();
-            if (lane == 0) {
-                if (bytes > 0) {
-                    mbar_arrive_expect_tx(&full[s], bytes);
-                    tma_load_1d(smem + p.L.stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
-                } else {
-                    mbar_arrive(&full[s]);
-                }
-                trace_ev(p, lane, 9, 2, v);
-                const int vp = v + NST + p.l2_ahead;
-                if (vp < NP) {
-                    const int64_t q0 = p.prow[p.panel_row[pan0 + vp]], q1 = p.prow[p.panel_row[pan0 + vp + 1]];
-                    if (q1 > q0) tma_prefetch_l2(gsrc + q0 * ES, (uint32_t)((q1 - q0) * ES));
-                }
-            }
-            if (++s == NST) { s = 0; ++k; }
-        }
+        producer_role<U>(p, smem, rowmeta, panelmeta, full, empty, r0, pan0, NP, lane);
     } else if (warp == NBW + 1) {
-        // =============================== chain ==============================================
-        const T eps = eps_of<T>();
-        const T dq = ma.dq;
-        typename Model::Lane L;
-        typename Model::Raw pend;                       // parameters of the lane's next column, in flight
-        bool has_pend = false;
-        T eo_pend = T(0);
-        {
-            typename Model::Raw r;
-            Model::load_raw(ma, r0 + lane, lane < B, r);
-            Model::derive(ma, r, L);
-            Model::load_raw(ma, r0 + lane, false, pend);
-        }
-        T eo = (lane < B) ? eta_s[lane] : T(0);
-        T X0 = T(0), X1 = T(0);
-        int j0 = 0, s = 0;
-        int rs_next = p.panel_row[pan0 + 1] - r0;
-        int need_c = p.panel_need[pan0];
-        for (int u = 0; u < NP; ++u) {
-            // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
-            const int nrows = rs_next - j0;
-            const int base = j0 & 31;
-            const int rel = (lane - base) & 31;
-            const int need_c_cur = need_c;
-            if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
-            trace_ev(p, lane, 8, 0, u);
-            wait_progress(prog, (uint32_t)(u + 1), (uint32_t)need_c_cur, lane);
-            trace_ev(p, lane, 8, 1, u);
-
-            // fold what the bulk warps prepared for this panel's columns
-            T bsum = T(0);
-            if (rel < nrows) {
-                const int cl = j0 + rel;
-#pragma unroll
-                for (int w = 0; w < NBW; ++w) bsum += partial[w * RR + (cl & (RR - 1))];
-                X0 += f_s[cl] + bsum;
-            }
-            T Xown = T(0);
-#pragma unroll
-            for (int h = 0; h < PMAX; h += 8) {
-                if (h < nrows) {
-                    T w0[8], w1[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
-                        const T* wr = wwin + ((j0 + h + i) & (RR - 1)) * WW;
-                        w0[i] = (h + i < nrows) ? wr[k0] : T(0);
-                        w1[i] = (h + i < nrows && k0 + 32 < WW) ? wr[k0 + 32] : T(0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (h + i < nrows) {
-                            T en, d;
-                            bool skip;
-                            typename Model::Out o;
-                            Model::step(L, X0, eo, eps, en, d, skip, o);
-                            const bool mine = (rel == h + i);
-                            Xown = mine ? X0 : Xown;
-                            const T a = shfl_t(en, (base + h + i) & 31);
-                            X0 = mine ? X1 : X0;
-                            X1 = mine ? T(0) : X1;
-                            X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
-                            X1 = fma_t(w1[i], a, X1);
-                        }
-                    }
-                }
-            }
-            trace_ev(p, lane, 8, 2, u);
-            // panel epilogue: outputs of the rows (re-evaluated from the saved X: same bits as on the chain),
-            // eta_new for the bulk axpy, parameters of the lanes' next columns
-            if (rel < nrows) {
-                T en, d;
-                bool skip;
-                typename Model::Out o;
-                Model::step(L, Xown, eo, eps, en, d, skip, o);
-                const int cl = j0 + rel;
-                const int row = r0 + cl;
-                Model::store(ma, row, skip, o);
-                if (!skip) sa.eta[row] = en;                                       // :431
-                sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
-                sa.q[row] = dq * (Xown - bsum);                                    // forward part of q (see header)
-                alpha[cl & (RR - 1)] = en;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cdone[s]);
-            trace_ev(p, lane, 8, 3, u);
-            if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; has_pend = false; }
-            if (rel < nrows) {
-                const int cn = j0 + rel + 32;
-                Model::load_raw(ma, r0 + cn, cn < B, pend);
-                eo_pend = (cn < B) ? eta_s[cn] : T(0);
-                has_pend = true;
-            }
-            j0 += nrows;
-            if (++s == NST) s = 0;
-        }
+        chain_role<T, Model, NBW, NBW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else {
         // =============================== bulk ===============================================
         const int wb = warp;
@@ -483,18 +544,7 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
             const int4 pm = panelmeta[s];
             const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
             // ---- window coefficients of the panel's rows (row r of the panel -> bulk warp r % NBW) ----
-            for (int r = wb; r < P; r += NBW) {
-                const int jl = jl0 + r;
-                const int4 m = rowmeta[jl & (RR - 1)];
-                const int cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
-#pragma unroll
-                for (int kk = lane; kk < WW; kk += WARP) {
-                    const int col = jl + 1 + kk;
-                    T v = T(0);
-                    if (col < cut && col / EPV >= m.y && col / EPV < m.z) v = ld_elem<T, U>(smem + m.x + col * ES);
-                    wwin[(jl & (RR - 1)) * WW + kk] = v;
-                }
-            }
+            for (int r = wb; r < P; r += NBW) window_row<T, U>(smem, rowmeta, sm.wwin, jl0 + r, lane);
             // ---- A(u): backward dots of the rows of panel u ----------------------------------
             for (int rg = 0; rg < P; rg += 4) {
                 const int nv = min(4, P - rg);

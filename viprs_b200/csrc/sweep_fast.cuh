@@ -1,0 +1,411 @@
+// viprs_b200 -- the register-resident variant of the one-pass sweep (float32 state, LD blocks <= 4096 SNPs).
+//
+// Same algorithm, hand-offs, producer and chain warp as sweep.cuh; what changes is where the block state
+// lives and how the bulk work is split:
+//   warps 0..3  "A" : backward dots B_j = sum_{k>j} R_jk eta_k(old).  Thread t owns the LD vectors
+//                     v = t + 128 c (c < NVT = 32/EPV) of every row and keeps eta_old of its 32 columns in
+//                     REGISTERS.  int8 LD: eta_old is held as NLIMB balanced base-128 digits (int8) of a
+//                     block-scaled fixed-point value and the dot is IDP.4A (dp4a, u8 x s8 -> exact int32)
+//                     on the raw biased bytes -- no dequantisation instruction at all on this side.
+//   warps 4..7  "C" : forward axpy f_k += R_jk eta_j(new) with the same vector ownership and f in REGISTERS;
+//                     columns whose accumulation is complete are published to a 128-entry ring for the chain.
+// No eta / f arrays in shared memory => the whole 113 KB (two CTAs per SM) minus ~20 KB goes to the TMA ring.
+#pragma once
+#include <type_traits>
+
+#include "sweep.cuh"
+
+namespace vb {
+
+constexpr int NAW = 4;                    // A warps
+constexpr int NCW = 4;                    // C warps
+constexpr int GT = 128;                   // threads per bulk group
+constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
+constexpr int FR = 128;                   // published-f ring (columns)
+constexpr int HP = 264;                   // row stride of the digit prefix sums (>= 4096/16 + 1)
+constexpr int NLIMB_MAX = 4;
+
+struct FastLayout {
+    uint32_t stages, rowmeta, panelmeta, partial, alpha, wwin, fring, hpre, red, bars, counters, total;
+};
+inline FastLayout make_fast_layout(int stage_bytes, int nst) {
+    FastLayout L;
+    uint32_t o = 0;
+    L.stages = o;    o += (uint32_t)nst * (uint32_t)stage_bytes;       o = align128(o);
+    L.rowmeta = o;   o += RR * (uint32_t)sizeof(int4);
+    L.panelmeta = o; o += NST_MAX * (uint32_t)sizeof(int4);
+    L.partial = o;   o += NAW * RR * 4;
+    L.alpha = o;     o += RR * 4;
+    L.wwin = o;      o += RR * WW * 4;
+    L.fring = o;     o += FR * 4;
+    L.hpre = o;      o += NLIMB_MAX * HP * 4;
+    L.red = o;       o += 64;
+    L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
+    L.counters = o;  o += (NAW + NCW) * (uint32_t)sizeof(uint32_t);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // sum_b u8(a.b) * s8(b.b) + c
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Reduce 16 per-lane accumulators across the warp with 16 shuffles: on return v[0] of lane l holds the warp
+// total of accumulator (l >> 1).
+template <typename T>
+__device__ __forceinline__ void warp_reduce16(T* v, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const T send = b4 ? v[i] : v[i + 8];
+        const T keep = b4 ? v[i + 8] : v[i];
+        v[i] = keep + shfl_xor_t(send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T send = b3 ? v[i] : v[i + 4];
+        const T keep = b3 ? v[i + 4] : v[i];
+        v[i] = keep + shfl_xor_t(send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = b2 ? v[i] : v[i + 2];
+        const T keep = b2 ? v[i + 2] : v[i];
+        v[i] = keep + shfl_xor_t(send, 4);
+    }
+    {
+        const T send = b1 ? v[0] : v[1];
+        const T keep = b1 ? v[1] : v[0];
+        v[0] = keep + shfl_xor_t(send, 2);
+    }
+    v[0] += shfl_xor_t(v[0], 1);
+}
+
+template <typename U, typename Model, int NLIMB>
+__global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
+                                                                              const typename Model::Args ma,
+                                                                              const StateArgs<float> sa) {
+    using T = float;
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int NVT = 32 / EPV;                        // LD vectors per thread per row
+    constexpr bool DP4A = std::is_same<U, int8_t>::value;
+    static_assert(NAW + NCW == NBW, "the chain / producer warps sit behind NBW bulk warps");
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    SmemView<T> sm;
+    sm.base = smem;
+    sm.rowmeta = reinterpret_cast<int4*>(smem + FL.rowmeta);
+    sm.panelmeta = reinterpret_cast<int4*>(smem + FL.panelmeta);
+    sm.partial = reinterpret_cast<T*>(smem + FL.partial);
+    sm.alpha = reinterpret_cast<T*>(smem + FL.alpha);
+    sm.wwin = reinterpret_cast<T*>(smem + FL.wwin);
+    sm.full = reinterpret_cast<uint64_t*>(smem + FL.bars);
+    sm.empty = sm.full + NST_MAX;
+    sm.cdone = sm.full + 2 * NST_MAX;
+    sm.prog = reinterpret_cast<uint32_t*>(smem + FL.counters);
+    T* fring = reinterpret_cast<T*>(smem + FL.fring);
+    sm.fsrc = fring;
+    sm.fmask = FR - 1;
+    int* hpre = reinterpret_cast<int*>(smem + FL.hpre);            // [NLIMB][HP] digit sums of the vectors before v
+    float* red = reinterpret_cast<float*>(smem + FL.red);
+
+    const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
+    const int blk = p.blk_order[blockIdx.x];
+    const int r0 = p.blk_row[blk], r1 = p.blk_row[blk + 1];
+    const int B = r1 - r0;
+    const int pan0 = p.blk_panel[blk];
+    const int NP = p.blk_panel[blk + 1] - pan0;
+    const int NST = p.nst;
+    const int nvec = (B + EPV - 1) / EPV;
+
+    // ---- prologue ----------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); mbar_init(&sm.cdone[s], 1); }
+        for (int w = 0; w < NAW + NCW; ++w) sm.prog[w] = 0;
+        fence_mbar_init();
+    }
+    for (int i = tid; i < FR; i += blockDim.x) fring[i] = 0.f;
+    // eta_old of the thread's columns -> registers (A warps); int8: block-scaled balanced base-128 digits
+    [[maybe_unused]] uint32_t hl[NVT][DP4A ? NLIMB : 1][4];
+    [[maybe_unused]] float es[DP4A ? 1 : NVT][DP4A ? 1 : EPV];
+    [[maybe_unused]] float bscale = 1.f;                 // block scale: a power of two >= max |eta_old|
+    if constexpr (DP4A) {
+        float mx = 0.f;
+        for (int i = tid; i < B; i += blockDim.x) mx = fmaxf(mx, fabsf(sa.eta[r0 + i]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = 0.f;
+        for (int w = 0; w < NBW + 2; ++w) mx = fmaxf(mx, red[w]);
+        int ex = 0;
+        if (mx > 0.f) frexpf(mx, &ex);                   // mx = m * 2^ex, m in [0.5, 1)
+        bscale = ldexpf(1.f, ex);
+        const float qs = ldexpf(1.f, 7 * NLIMB - 1 - ex);        // eta / bscale * 2^(7 NLIMB - 1), exact scaling
+        if (tid < GT) {
+#pragma unroll
+            for (int c = 0; c < NVT; ++c) {
+                const int v = tid + GT * c;
+                int dsum[NLIMB];
+#pragma unroll
+                for (int l = 0; l < NLIMB; ++l) {
+                    dsum[l] = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) hl[c][l][w] = 0;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int col = v * 16 + e;
+                    const float x = (col < B) ? sa.eta[r0 + col] : 0.f;
+                    int Q = __float2int_rn(x * qs);                          // |Q| <= 2^(7 NLIMB - 1)
+#pragma unroll
+                    for (int l = NLIMB - 1; l >= 0; --l) {
+                        int d;
+                        if (l > 0) { d = ((Q + 64) & 127) - 64; Q = (Q - d) >> 7; } else { d = Q; }
+                        dsum[l] += d;
+                        hl[c][l][e >> 2] |= (uint32_t)(d & 0xff) << (8 * (e & 3));
+                    }
+                }
+                if (v < HP - 1) {
+#pragma unroll
+                    for (int l = 0; l < NLIMB; ++l) hpre[l * HP + v + 1] = dsum[l];
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < NLIMB) {
+            // inclusive scan of hpre[warp][1..256] (8 entries per lane), hpre[warp][0] = 0
+            int* hp = hpre + warp * HP;
+            int loc[8];
+            int run = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { run += hp[1 + lane * 8 + i]; loc[i] = run; }
+            int tot = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, tot, o);
+                if (lane >= o) tot += n;
+            }
+            const int excl = tot - run;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hp[1 + lane * 8 + i] = loc[i] + excl;
+            if (lane == 0) hp[0] = 0;
+        }
+    } else {
+        if (tid < GT) {
+#pragma unroll
+            for (int c = 0; c < NVT; ++c) {
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    const int col = (tid + GT * c) * EPV + e;
+                    es[c][e] = (col < B) ? sa.eta[r0 + col] : 0.f;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    if (warp == NBW) {
+        producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane);
+    } else if (warp == NBW + 1) {
+        chain_role<T, Model, NAW, NCW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
+    } else if (warp < NAW) {
+        // =============================== A: backward dots =====================================
+        const int wa = warp;
+        const int t = tid;                                   // 0..127
+        int s = 0, k = 0;
+        for (int u = 0; u < NP; ++u) {
+            trace_ev(p, lane, wa, 0, u);
+            mbar_wait(&sm.full[s], k & 1);
+            trace_ev(p, lane, wa, 1, u);
+            const int4 pm = sm.panelmeta[s];
+            const int P = pm.x, jl0 = pm.w;
+            for (int r = wa; r < P; r += NAW) window_row<T, U>(smem, sm.rowmeta, sm.wwin, jl0 + r, lane);
+            for (int rg = 0; rg < P; rg += 4) {
+                const int nv = min(4, P - rg);
+                int mx[4], my[4], mz[4];
+                int lo_all = 0, hi_all = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    mx[r] = 0; my[r] = 0; mz[r] = 0;
+                    if (r < nv) {
+                        const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
+                        mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                        lo_all = max(lo_all, m.y); hi_all = min(hi_all, m.z);
+                    }
+                }
+                if constexpr (DP4A) {
+                    int acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = 0;
+#pragma unroll
+                    for (int c = 0; c < NVT; ++c) {
+                        const int v = t + GT * c;
+                        if (v >= lo_all && v < hi_all) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                if (r < nv) {
+                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+#pragma unroll
+                                    for (int l = 0; l < NLIMB; ++l) {
+                                        int a = acc[r * 4 + l];
+                                        a = dp4a_us(cv.x, hl[c][l][0], a);
+                                        a = dp4a_us(cv.y, hl[c][l][1], a);
+                                        a = dp4a_us(cv.z, hl[c][l][2], a);
+                                        a = dp4a_us(cv.w, hl[c][l][3], a);
+                                        acc[r * 4 + l] = a;
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                if (v >= my[r] && v < mz[r]) {
+                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+#pragma unroll
+                                    for (int l = 0; l < NLIMB; ++l) {
+                                        int a = acc[r * 4 + l];
+                                        a = dp4a_us(cv.x, hl[c][l][0], a);
+                                        a = dp4a_us(cv.y, hl[c][l][1], a);
+                                        a = dp4a_us(cv.z, hl[c][l][2], a);
+                                        a = dp4a_us(cv.w, hl[c][l][3], a);
+                                        acc[r * 4 + l] = a;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    warp_reduce16(acc, lane);
+                    // lane holds sum_b u8 * digit for (row r, limb l); sum u*h = sum code*h + 128 * sum h over the
+                    // packed range of the row.  The range correction is applied once per row (by A warp 0).
+                    const int idx = lane >> 1, r = idx >> 2, l = idx & 3;
+                    double term = 0.0;
+                    if (r < nv && l < NLIMB) {
+                        int S = acc[0];
+                        if (wa == 0) {
+                            const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
+                            S -= 128 * (hpre[l * HP + min(m.z, HP - 1)] - hpre[l * HP + min(m.y, HP - 1)]);
+                        }
+                        // digit l has weight 128^(NLIMB-1-l) * 2^-(7 NLIMB - 1) = 2^(-7 l - 6)
+                        term = (double)S * (double)ldexpf(bscale, -7 * l - 6);
+                    }
+                    term += shfl_xor_t(term, 2);
+                    term += shfl_xor_t(term, 4);
+                    if ((lane & 7) == 0 && r < nv) sm.partial[wa * RR + ((jl0 + rg + r) & (RR - 1))] = (float)term;
+                } else {
+                    typename Pk<T>::acc_t acc2[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc2[r] = Pk<T>::zero();
+#pragma unroll
+                    for (int c = 0; c < NVT; ++c) {
+                        const int v = t + GT * c;
+                        if (v >= lo_all && v < hi_all) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                if (r < nv) {
+                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+                                    VecOps<T, U>::dot(cv, es[c], acc2[r]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                if (v >= my[r] && v < mz[r]) {
+                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
+                                    VecOps<T, U>::dot(cv, es[c], acc2[r]);
+                                }
+                            }
+                        }
+                    }
+                    T acc[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] = Pk<T>::sum(acc2[r]);
+                    const int rr = warp_reduce4(acc, lane);
+                    if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc[0];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) st_release(&sm.prog[wa], (uint32_t)(u + 1));
+            trace_ev(p, lane, wa, 2, u);
+            if (++s == NST) { s = 0; ++k; }
+        }
+    } else {
+        // =============================== C: forward axpy ======================================
+        const int wc = warp - NAW;
+        const int t = tid - GT;                              // 0..127
+        float f[NVT][EPV];
+#pragma unroll
+        for (int c = 0; c < NVT; ++c)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) f[c][e] = 0.f;
+        int pubvec = 0;                                      // vectors below this index have been published
+        int s = 0, k = 0;
+        for (int v = 0; v < NP; ++v) {
+            mbar_wait(&sm.cdone[s], k & 1);
+            trace_ev(p, lane, NAW + wc, 4, v);
+            const int4 pm = sm.panelmeta[s];
+            const int Pc = pm.x, jl0 = pm.w;
+            const int last_cut = (jl0 + Pc - 1 + WIN + EPV - 1) / EPV;      // cut vector of the panel's last row
+            for (int rg = 0; rg < Pc; rg += 4) {
+                const int nv = min(4, Pc - rg);
+                int mx[4], my[4], mz[4];
+                T al[4];
+                int lo_all = last_cut, hi_all = 0x7fffffff;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
+                    if (r < nv) {
+                        const int jl = jl0 + rg + r;
+                        const int4 m = sm.rowmeta[jl & (RR - 1)];
+                        mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
+                        al[r] = sm.alpha[jl & (RR - 1)];
+                        lo_all = max(lo_all, my[r]); hi_all = min(hi_all, mz[r]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NVT; ++c) {
+                    const int vv = t + GT * c;
+                    if (vv >= lo_all && vv < hi_all) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < nv) {
+                                const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
+                                VecOps<T, U>::axpy(cv, al[r], f[c]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (vv >= my[r] && vv < mz[r]) {
+                                const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
+                                VecOps<T, U>::axpy(cv, al[r], f[c]);
+                            }
+                        }
+                    }
+                }
+            }
+            // columns below cut(first row after the panel) are complete: publish them for the chain
+            const int newpub = min(nvec, (jl0 + Pc + WIN + EPV - 1) / EPV);
+#pragma unroll
+            for (int c = 0; c < NVT; ++c) {
+                const int vv = t + GT * c;
+                if (vv >= pubvec && vv < newpub) {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) fring[(vv * EPV + e) & (FR - 1)] = f[c][e];
+                }
+            }
+            pubvec = max(pubvec, newpub);
+            __syncwarp();
+            if (lane == 0) {
+                st_release(&sm.prog[NAW + wc], (uint32_t)(v + 1));
+                mbar_arrive(&sm.empty[s]);
+            }
+            trace_ev(p, lane, NAW + wc, 5, v);
+            if (++s == NST) { s = 0; ++k; }
+        }
+    }
+}
+
+}  // namespace vb
