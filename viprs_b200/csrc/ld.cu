@@ -243,13 +243,19 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
             const int r0 = blk_row[b], r1 = blk_row[b + 1];
             const int first_panel = (int)panel_row.size();
             blk_panel[b] = first_panel;
-            int64_t pbytes = 0; int prows = 0;
-            for (int j = r0; j < r1; ++j) {
-                const int64_t rb = (prow[j + 1] - prow[j]) * esize;
-                if (prows == 0 || prows == vb::PMAX || pbytes + rb > stage_bytes) {
-                    panel_row.push_back(j); prows = 0; pbytes = 0;
+            // greedy cut: as many rows as fit one stage (<= PMAX), rounded down to a multiple of 4 because the
+            // bulk warps work on groups of 4 rows (a 5-row panel would cost them as much as an 8-row one)
+            int j = r0;
+            while (j < r1) {
+                int64_t pbytes = 0; int prows = 0;
+                while (j + prows < r1 && prows < vb::PMAX) {
+                    const int64_t rb = (prow[j + prows + 1] - prow[j + prows]) * esize;
+                    if (prows > 0 && pbytes + rb > stage_bytes) break;
+                    pbytes += rb; ++prows;
                 }
-                ++prows; pbytes += rb;
+                if (prows > 4 && j + prows < r1) prows &= ~3;
+                panel_row.push_back(j);
+                j += prows;
             }
             // panel u = rows [ps, pe): its columns need the bulk axpy of every row <= pe-1-WIN, i.e. of
             // every panel up to the one holding that row (which always ends before ps because PMAX <= WIN/2)

@@ -293,6 +293,8 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
     const int NST = p.nst;
     const T eps = eps_of<T>();
     const T dq = ma.dq;
+    const uint32_t a_partial = smem_u32(sm.partial), a_wwin = smem_u32(sm.wwin), a_alpha = smem_u32(sm.alpha),
+                   a_f = smem_u32(sm.fsrc);
     typename Model::Lane L;
     typename Model::Raw pend;                       // parameters of the lane's next column, in flight
     bool has_pend = false;
@@ -324,8 +326,8 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
         if (rel < nrows) {
             const int cl = j0 + rel;
 #pragma unroll
-            for (int w = 0; w < NA; ++w) bsum += sm.partial[w * RR + (cl & (RR - 1))];
-            X0 += sm.fsrc[cl & sm.fmask] + bsum;
+            for (int w = 0; w < NA; ++w) bsum += lds_t(a_partial + (uint32_t)(w * RR + (cl & (RR - 1))) * sizeof(T), T());
+            X0 += lds_t(a_f + (uint32_t)(cl & sm.fmask) * sizeof(T), T()) + bsum;
         }
         T Xown = T(0);
 #pragma unroll
@@ -335,9 +337,10 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
-                    const T* wr = sm.wwin + ((j0 + h + i) & (RR - 1)) * WW;
-                    w0[i] = (h + i < nrows) ? wr[k0] : T(0);
-                    w1[i] = (h + i < nrows && k0 + 32 < WW) ? wr[k0 + 32] : T(0);
+                    const uint32_t wr = a_wwin + (uint32_t)((((j0 + h + i) & (RR - 1)) * WW + k0) * sizeof(T));
+                    w0[i] = T(0); w1[i] = T(0);
+                    if (h + i < nrows) w0[i] = lds_t(wr, T());
+                    if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_t(wr + 32 * sizeof(T), T());
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -371,7 +374,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             if (!skip) sa.eta[row] = en;                                       // :431
             sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
             sa.q[row] = dq * (Xown - bsum);                                    // forward part of q (see header)
-            sm.alpha[cl & (RR - 1)] = en;
+            sts_t(a_alpha + (uint32_t)(cl & (RR - 1)) * sizeof(T), en);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.cdone[s]);

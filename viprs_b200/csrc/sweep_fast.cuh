@@ -22,11 +22,11 @@ constexpr int NCW = 4;                    // C warps
 constexpr int GT = 128;                   // threads per bulk group
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
-constexpr int HP = 264;                   // row stride of the digit prefix sums (>= 4096/16 + 1)
+constexpr int HP = 264;                   // entries of the fixed-point prefix sum (>= 4096/16 + 1)
 constexpr int NLIMB_MAX = 4;
 
 struct FastLayout {
-    uint32_t stages, rowmeta, panelmeta, partial, alpha, wwin, fring, hpre, red, bars, counters, total;
+    uint32_t stages, rowmeta, panelmeta, partial, alpha, wwin, fring, hc, zero, red, bars, counters, total;
 };
 inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     FastLayout L;
@@ -38,7 +38,8 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     L.alpha = o;     o += RR * 4;
     L.wwin = o;      o += RR * WW * 4;
     L.fring = o;     o += FR * 4;
-    L.hpre = o;      o += NLIMB_MAX * HP * 4;
+    L.hc = o;        o += HP * 8;
+    L.zero = o;      o += 32;
     L.red = o;       o += 64;
     L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
     L.counters = o;  o += (NAW + NCW) * (uint32_t)sizeof(uint32_t);
@@ -50,37 +51,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // 
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
-}
-
-// Reduce 16 per-lane accumulators across the warp with 16 shuffles: on return v[0] of lane l holds the warp
-// total of accumulator (l >> 1).
-template <typename T>
-__device__ __forceinline__ void warp_reduce16(T* v, int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const T send = b4 ? v[i] : v[i + 8];
-        const T keep = b4 ? v[i + 8] : v[i];
-        v[i] = keep + shfl_xor_t(send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const T send = b3 ? v[i] : v[i + 4];
-        const T keep = b3 ? v[i + 4] : v[i];
-        v[i] = keep + shfl_xor_t(send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const T send = b2 ? v[i] : v[i + 2];
-        const T keep = b2 ? v[i + 2] : v[i];
-        v[i] = keep + shfl_xor_t(send, 4);
-    }
-    {
-        const T send = b1 ? v[0] : v[1];
-        const T keep = b1 ? v[1] : v[0];
-        v[0] = keep + shfl_xor_t(send, 2);
-    }
-    v[0] += shfl_xor_t(v[0], 1);
 }
 
 template <typename U, typename Model, int NLIMB>
@@ -108,8 +78,12 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
     T* fring = reinterpret_cast<T*>(smem + FL.fring);
     sm.fsrc = fring;
     sm.fmask = FR - 1;
-    int* hpre = reinterpret_cast<int*>(smem + FL.hpre);            // [NLIMB][HP] digit sums of the vectors before v
+    long long* hc = reinterpret_cast<long long*>(smem + FL.hc);    // [HP] sum of the fixed-point eta_old of the columns before vector v
+    uint32_t* zvec = reinterpret_cast<uint32_t*>(smem + FL.zero);  // 16 B of zeros | 16 B of "code 0" in the biased encoding
     float* red = reinterpret_cast<float*>(smem + FL.red);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t zaddr_raw = sbase + FL.zero;          // bytes 0x00: contribute nothing to a dp4a
+    const uint32_t zaddr_code = sbase + FL.zero + 16;    // code 0: contributes nothing to a decoded dot / axpy
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int blk = p.blk_order[blockIdx.x];
@@ -127,10 +101,12 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         fence_mbar_init();
     }
     for (int i = tid; i < FR; i += blockDim.x) fring[i] = 0.f;
+    if (tid < 4) zvec[tid] = 0u;
+    else if (tid < 8) zvec[tid] = sizeof(U) == 1 ? 0x80808080u : (sizeof(U) == 2 && !std::is_floating_point<U>::value ? 0x80008000u : 0u);
     // eta_old of the thread's columns -> registers (A warps); int8: block-scaled balanced base-128 digits
     [[maybe_unused]] uint32_t hl[NVT][DP4A ? NLIMB : 1][4];
     [[maybe_unused]] float es[DP4A ? 1 : NVT][DP4A ? 1 : EPV];
-    [[maybe_unused]] float bscale = 1.f;                 // block scale: a power of two >= max |eta_old|
+    [[maybe_unused]] double wscale = 1.0;                // value of one fixed-point unit: bscale * 2^-(7 NLIMB - 1)
     if constexpr (DP4A) {
         float mx = 0.f;
         for (int i = tid; i < B; i += blockDim.x) mx = fmaxf(mx, fabsf(sa.eta[r0 + i]));
@@ -141,57 +117,51 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         mx = 0.f;
         for (int w = 0; w < NBW + 2; ++w) mx = fmaxf(mx, red[w]);
         int ex = 0;
-        if (mx > 0.f) frexpf(mx, &ex);                   // mx = m * 2^ex, m in [0.5, 1)
-        bscale = ldexpf(1.f, ex);
-        const float qs = ldexpf(1.f, 7 * NLIMB - 1 - ex);        // eta / bscale * 2^(7 NLIMB - 1), exact scaling
+        if (mx > 0.f) frexpf(mx, &ex);                   // mx = m * 2^ex, m in [0.5, 1): block scale 2^ex > max |eta_old|
+        const float qs = ldexpf(1.f, 7 * NLIMB - 1 - ex);        // eta -> fixed point Q, |Q| <= 2^(7 NLIMB - 1); exact scaling
+        wscale = ldexp(1.0, ex - (7 * NLIMB - 1));
         if (tid < GT) {
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
                 const int v = tid + GT * c;
-                int dsum[NLIMB];
+                long long qsum = 0;
 #pragma unroll
-                for (int l = 0; l < NLIMB; ++l) {
-                    dsum[l] = 0;
+                for (int l = 0; l < NLIMB; ++l)
 #pragma unroll
                     for (int w = 0; w < 4; ++w) hl[c][l][w] = 0;
-                }
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int col = v * 16 + e;
                     const float x = (col < B) ? sa.eta[r0 + col] : 0.f;
-                    int Q = __float2int_rn(x * qs);                          // |Q| <= 2^(7 NLIMB - 1)
+                    int Q = __float2int_rn(x * qs);
+                    qsum += Q;
 #pragma unroll
-                    for (int l = NLIMB - 1; l >= 0; --l) {
+                    for (int l = NLIMB - 1; l >= 0; --l) {           // Q = sum_l d_l 128^(NLIMB-1-l), d_l in [-64, 64]
                         int d;
                         if (l > 0) { d = ((Q + 64) & 127) - 64; Q = (Q - d) >> 7; } else { d = Q; }
-                        dsum[l] += d;
                         hl[c][l][e >> 2] |= (uint32_t)(d & 0xff) << (8 * (e & 3));
                     }
                 }
-                if (v < HP - 1) {
-#pragma unroll
-                    for (int l = 0; l < NLIMB; ++l) hpre[l * HP + v + 1] = dsum[l];
-                }
+                if (v < HP - 1) hc[v + 1] = qsum;
             }
         }
         __syncthreads();
-        if (warp < NLIMB) {
-            // inclusive scan of hpre[warp][1..256] (8 entries per lane), hpre[warp][0] = 0
-            int* hp = hpre + warp * HP;
-            int loc[8];
-            int run = 0;
+        if (warp == 0) {
+            // inclusive scan of hc[1..256] (8 entries per lane), hc[0] = 0
+            long long loc[8];
+            long long run = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { run += hp[1 + lane * 8 + i]; loc[i] = run; }
-            int tot = run;
+            for (int i = 0; i < 8; ++i) { run += hc[1 + lane * 8 + i]; loc[i] = run; }
+            long long tot = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, tot, o);
+                const long long n = __shfl_up_sync(0xffffffffu, tot, o);
                 if (lane >= o) tot += n;
             }
-            const int excl = tot - run;
+            const long long excl = tot - run;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hp[1 + lane * 8 + i] = loc[i] + excl;
-            if (lane == 0) hp[0] = 0;
+            for (int i = 0; i < 8; ++i) hc[1 + lane * 8 + i] = loc[i] + excl;
+            if (lane == 0) hc[0] = 0;
         }
     } else {
         if (tid < GT) {
@@ -213,8 +183,10 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         chain_role<T, Model, NAW, NCW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else if (warp < NAW) {
         // =============================== A: backward dots =====================================
+        // Branch-free inner loop: a (row, vector) pair outside the row's range reads a 16-byte zero vector.
         const int wa = warp;
         const int t = tid;                                   // 0..127
+        const uint32_t zaddr = DP4A ? zaddr_raw : zaddr_code;
         int s = 0, k = 0;
         for (int u = 0; u < NP; ++u) {
             trace_ev(p, lane, wa, 0, u);
@@ -223,107 +195,84 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
             const int4 pm = sm.panelmeta[s];
             const int P = pm.x, jl0 = pm.w;
             for (int r = wa; r < P; r += NAW) window_row<T, U>(smem, sm.rowmeta, sm.wwin, jl0 + r, lane);
+#pragma unroll 1
             for (int rg = 0; rg < P; rg += 4) {
                 const int nv = min(4, P - rg);
                 int mx[4], my[4], mz[4];
-                int lo_all = 0, hi_all = 0x7fffffff;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     mx[r] = 0; my[r] = 0; mz[r] = 0;
                     if (r < nv) {
                         const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
                         mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
-                        lo_all = max(lo_all, m.y); hi_all = min(hi_all, m.z);
+                    }
+                }
+                [[maybe_unused]] int acc[4][DP4A ? NLIMB : 1];
+                [[maybe_unused]] typename Pk<T>::acc_t acc2[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc2[r] = Pk<T>::zero();
+#pragma unroll
+                    for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) acc[r][l] = 0;
+                }
+#pragma unroll
+                for (int c = 0; c < NVT; ++c) {
+                    const int v = t + GT * c;
+                    uint32_t ad[4];
+                    bool any = false;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const bool in = (v >= my[r]) && (v < mz[r]);
+                        any |= in;
+                        ad[r] = in ? sbase + (uint32_t)(mx[r] + v * 16) : zaddr;
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;         // no lane of the warp owns a live vector here
+                    uint4 cv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if constexpr (DP4A) {
+#pragma unroll
+                            for (int l = 0; l < NLIMB; ++l) {
+                                int a = acc[r][l];
+                                a = dp4a_us(cv[r].x, hl[c][l][0], a);
+                                a = dp4a_us(cv[r].y, hl[c][l][1], a);
+                                a = dp4a_us(cv[r].z, hl[c][l][2], a);
+                                a = dp4a_us(cv[r].w, hl[c][l][3], a);
+                                acc[r][l] = a;
+                            }
+                        } else {
+                            VecOps<T, U>::dot(cv[r], es[c], acc2[r]);
+                        }
                     }
                 }
                 if constexpr (DP4A) {
-                    int acc[16];
+                    // exact integer totals: REDUX per (row, digit), digits recombined in int64.
+                    // sum_b u8 * digit = sum code * digit + 128 * sum digit over the row's packed range; the range
+                    // term (128 * sum of Q over the range, from the prefix array) is removed once per row, by warp 0.
+                    long long V[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = 0;
+                    for (int r = 0; r < 4; ++r) {
+                        long long x = 0;
 #pragma unroll
-                    for (int c = 0; c < NVT; ++c) {
-                        const int v = t + GT * c;
-                        if (v >= lo_all && v < hi_all) {
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (r < nv) {
-                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
-#pragma unroll
-                                    for (int l = 0; l < NLIMB; ++l) {
-                                        int a = acc[r * 4 + l];
-                                        a = dp4a_us(cv.x, hl[c][l][0], a);
-                                        a = dp4a_us(cv.y, hl[c][l][1], a);
-                                        a = dp4a_us(cv.z, hl[c][l][2], a);
-                                        a = dp4a_us(cv.w, hl[c][l][3], a);
-                                        acc[r * 4 + l] = a;
-                                    }
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (v >= my[r] && v < mz[r]) {
-                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
-#pragma unroll
-                                    for (int l = 0; l < NLIMB; ++l) {
-                                        int a = acc[r * 4 + l];
-                                        a = dp4a_us(cv.x, hl[c][l][0], a);
-                                        a = dp4a_us(cv.y, hl[c][l][1], a);
-                                        a = dp4a_us(cv.z, hl[c][l][2], a);
-                                        a = dp4a_us(cv.w, hl[c][l][3], a);
-                                        acc[r * 4 + l] = a;
-                                    }
-                                }
-                            }
-                        }
+                        for (int l = 0; l < NLIMB; ++l) x = x * 128 + (long long)__reduce_add_sync(0xffffffffu, acc[r][l]);
+                        V[r] = x;
                     }
-                    warp_reduce16(acc, lane);
-                    // lane holds sum_b u8 * digit for (row r, limb l); sum u*h = sum code*h + 128 * sum h over the
-                    // packed range of the row.  The range correction is applied once per row (by A warp 0).
-                    const int idx = lane >> 1, r = idx >> 2, l = idx & 3;
-                    double term = 0.0;
-                    if (r < nv && l < NLIMB) {
-                        int S = acc[0];
+                    if (lane < nv) {
+                        long long x = lane == 0 ? V[0] : lane == 1 ? V[1] : lane == 2 ? V[2] : V[3];
                         if (wa == 0) {
-                            const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
-                            S -= 128 * (hpre[l * HP + min(m.z, HP - 1)] - hpre[l * HP + min(m.y, HP - 1)]);
+                            const int4 m = sm.rowmeta[(jl0 + rg + lane) & (RR - 1)];
+                            x -= 128 * (hc[min(m.z, HP - 1)] - hc[min(m.y, HP - 1)]);
                         }
-                        // digit l has weight 128^(NLIMB-1-l) * 2^-(7 NLIMB - 1) = 2^(-7 l - 6)
-                        term = (double)S * (double)ldexpf(bscale, -7 * l - 6);
+                        sm.partial[wa * RR + ((jl0 + rg + lane) & (RR - 1))] = (float)((double)x * wscale);
                     }
-                    term += shfl_xor_t(term, 2);
-                    term += shfl_xor_t(term, 4);
-                    if ((lane & 7) == 0 && r < nv) sm.partial[wa * RR + ((jl0 + rg + r) & (RR - 1))] = (float)term;
                 } else {
-                    typename Pk<T>::acc_t acc2[4];
+                    T acc1[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) acc2[r] = Pk<T>::zero();
-#pragma unroll
-                    for (int c = 0; c < NVT; ++c) {
-                        const int v = t + GT * c;
-                        if (v >= lo_all && v < hi_all) {
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (r < nv) {
-                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
-                                    VecOps<T, U>::dot(cv, es[c], acc2[r]);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (v >= my[r] && v < mz[r]) {
-                                    const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + v * 16);
-                                    VecOps<T, U>::dot(cv, es[c], acc2[r]);
-                                }
-                            }
-                        }
-                    }
-                    T acc[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[r] = Pk<T>::sum(acc2[r]);
-                    const int rr = warp_reduce4(acc, lane);
-                    if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc[0];
+                    for (int r = 0; r < 4; ++r) acc1[r] = Pk<T>::sum(acc2[r]);
+                    const int rr = warp_reduce4(acc1, lane);
+                    if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc1[0];
                 }
             }
             __syncwarp();
@@ -347,12 +296,11 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
             trace_ev(p, lane, NAW + wc, 4, v);
             const int4 pm = sm.panelmeta[s];
             const int Pc = pm.x, jl0 = pm.w;
-            const int last_cut = (jl0 + Pc - 1 + WIN + EPV - 1) / EPV;      // cut vector of the panel's last row
+#pragma unroll 1
             for (int rg = 0; rg < Pc; rg += 4) {
                 const int nv = min(4, Pc - rg);
                 int mx[4], my[4], mz[4];
                 T al[4];
-                int lo_all = last_cut, hi_all = 0x7fffffff;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
@@ -361,29 +309,25 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
                         const int4 m = sm.rowmeta[jl & (RR - 1)];
                         mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
                         al[r] = sm.alpha[jl & (RR - 1)];
-                        lo_all = max(lo_all, my[r]); hi_all = min(hi_all, mz[r]);
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < NVT; ++c) {
                     const int vv = t + GT * c;
-                    if (vv >= lo_all && vv < hi_all) {
+                    uint32_t ad[4];
+                    bool any = false;
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (r < nv) {
-                                const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
-                                VecOps<T, U>::axpy(cv, al[r], f[c]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (vv >= my[r] && vv < mz[r]) {
-                                const uint4 cv = *reinterpret_cast<const uint4*>(smem + mx[r] + vv * 16);
-                                VecOps<T, U>::axpy(cv, al[r], f[c]);
-                            }
-                        }
+                    for (int r = 0; r < 4; ++r) {
+                        const bool in = (vv >= my[r]) && (vv < mz[r]);
+                        any |= in;
+                        ad[r] = in ? sbase + (uint32_t)(mx[r] + vv * 16) : zaddr_code;
                     }
+                    if (!__any_sync(0xffffffffu, any)) continue;
+                    uint4 cv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) VecOps<T, U>::axpy(cv[r], al[r], f[c]);
                 }
             }
             // columns below cut(first row after the panel) are complete: publish them for the chain
