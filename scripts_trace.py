@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 NP_ = 4096
-a = np.fromfile(sys.argv[1], dtype=np.uint64).astype(np.int64).reshape(10, 8, NP_)
+a = np.fromfile(sys.argv[1], dtype=np.uint64).astype(np.int64).reshape(-1, 8, NP_)
 t0 = a[a > 0].min()
 fast = a[4, 4].any() and not a[0, 4].any()          # fast kernel: warps 0-3 only A, 4-7 only C
 AW = range(4) if fast else range(8)

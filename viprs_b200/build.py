@@ -29,11 +29,13 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
+    extra = ["-DVB_TRACE"] if os.environ.get("VIPRS_B200_BUILD_TRACE") else []
+    extra += os.environ.get("VIPRS_B200_BUILD_DEFS", "").split()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
     for cmd, p in procs:

@@ -74,7 +74,7 @@ static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
-        kern<<<ld->n_blocks, (NBW + 2) * WARP, FL.total, st>>>(pp, FL, ma, sa);
+        kern<<<ld->n_blocks, FAST_WARPS * WARP, FL.total, st>>>(pp, FL, ma, sa);
     });
 }
 
@@ -91,7 +91,7 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
     if constexpr (sizeof(T) == 4 && !Model::kHeavy && sizeof(U) != 8) {
         if (fast_path_ok<T, U, Model>(ld)) {
             make_plan(ld, (int)sizeof(T), p, g);        // ring fields are overridden by the fast launcher
-            if (std::is_same<U, int8_t>::value && env_int("VIPRS_B200_LIMBS", 4) == 3)
+            if (std::is_same<U, int8_t>::value && env_int("VIPRS_B200_LIMBS", 3) == 3)
                 return launch_fast_one<U, Model, 3>(ld, p, ma, sa, st);
             return launch_fast_one<U, Model, 4>(ld, p, ma, sa, st);
         }

@@ -77,13 +77,18 @@ struct SweepPlan {                 // what ld.cu prepared (device pointers) + th
     SmemLayout L;
 };
 
-// debug timeline of CTA 0: trace[(role * 8 + ev) * kTracePanels + panel] = clock64()   (plain stores, no atomics)
+// debug timeline of CTA 0 (build with -DVB_TRACE, run with VIPRS_B200_TRACE=<file>):
+// trace[(role * 8 + ev) * kTracePanels + panel] = clock64()   (plain stores, no atomics)
 constexpr int kTracePanels = 4096;
-constexpr int kTraceSlots = 10 * 8 * kTracePanels;
+constexpr int kTraceSlots = 12 * 8 * kTracePanels;
+#ifdef VB_TRACE
 __device__ __forceinline__ void trace_ev(const SweepPlan& p, int lane, int role, int ev, int panel) {
     if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && panel < kTracePanels)
         p.trace[(role * 8 + ev) * kTracePanels + panel] = (unsigned long long)clock64();
 }
+#else
+__device__ __forceinline__ void trace_ev(const SweepPlan&, int, int, int, int) {}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // per-SNP update models (the chain warp's scalar math)
@@ -97,7 +102,7 @@ struct SlabModel {
     };
     static constexpr bool kHeavy = false;
     struct Raw { T beta, mm, sv, ul; };
-    struct Lane { T c0, c1, sv, ul; };
+    struct Lane { T c0, c1, a0, a1, ul; };      // mu = c1 X + c0 ;  sqrt(tau/2) mu = a1 X + a0
     struct Out { T mu, g; };
     static __device__ __forceinline__ void load_raw(const Args& a, int row, bool ok, Raw& r) {
         r.beta = T(0); r.mm = T(0); r.sv = T(0); r.ul = T(0);
@@ -106,12 +111,14 @@ struct SlabModel {
     static __device__ __forceinline__ void derive(const Args& a, const Raw& r, Lane& L) {
         L.c0 = mul_t(r.mm, r.beta);          // mu = fma(mu_mult, beta, -mu_mult*q)   (:401)  with q = dq * X
         L.c1 = -mul_t(r.mm, a.dq);
-        L.sv = r.sv; L.ul = r.ul;
+        L.a0 = mul_t(r.sv, L.c0);            // u = sqrt_half_var_tau * mu  (:404), one FMA off X instead of two ops
+        L.a1 = mul_t(r.sv, L.c1);
+        L.ul = r.ul;
     }
     // X: F_j + B_j in LD-code units; eo: eta_j before the update
     static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
         const T mu = fma_t(L.c1, X, L.c0);
-        const T uu = mul_t(L.sv, mu);                             // :404
+        const T uu = fma_t(L.a1, X, L.a0);                        // :404
         const T g = sigmoid_t(fma_t(uu, uu, L.ul));               // :405
         d = fma_t(g, mu, -eo);                                    // :408
         skip = abs_t(d) < eps;                                    // :410-413
@@ -211,7 +218,7 @@ template <typename T> __device__ __forceinline__ void load_state_vec(const T* sr
 template <typename T>
 struct SmemView {
     unsigned char* base;
-    int4* rowmeta;      // [RR] {byte offset of column 0 of the row, vs, ve, -}
+    int4* rowmeta;      // [RR] {byte offset of column 0 of the row, vs, ve, C-complete panels the NEXT panel needs}
     int4* panelmeta;    // [NST] {P, vmin, vmax, first local row}
     T* partial;         // [n_A_warps][RR] backward-dot partials
     T* alpha;           // [RR] eta_new of finished rows
@@ -247,6 +254,7 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
         int64_t o0 = 0, o1 = 0;
         int c = 0;
         if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
+        const int need_next = (v + 1 < NP) ? p.panel_need[pan0 + v + 1] : 0;   // what the chain needs before panel v+1
         trace_ev(p, lane, 9, 0, v);
         if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
         trace_ev(p, lane, 9, 1, v);
@@ -256,7 +264,7 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
             const int vs_r = c / EPV;
             int4 m;
             m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
-            m.y = vs_r; m.z = vs_r + nv; m.w = 0;
+            m.y = vs_r; m.z = vs_r + nv; m.w = need_next;
             rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
             if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
         }
@@ -307,19 +315,18 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
     }
     T eo = (lane < B) ? sa.eta[r0 + lane] : T(0);
     T X0 = T(0), X1 = T(0);
+    const uint32_t a_rowmeta = smem_u32(sm.rowmeta), a_panelmeta = smem_u32(sm.panelmeta);
     int j0 = 0, s = 0;
-    int rs_next = p.panel_row[pan0 + 1] - r0;
-    int need_c = p.panel_need[pan0];
+    int need_c = 0;                                  // the first panel has no predecessors
     for (int u = 0; u < NP; ++u) {
         // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
-        const int nrows = rs_next - j0;
+        trace_ev(p, lane, 8, 0, u);
+        wait_progress<NA, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c, lane);
+        trace_ev(p, lane, 8, 1, u);
+        const int nrows = (int)lds128(a_panelmeta + s * 16).x;
+        need_c = (int)lds128(a_rowmeta + (j0 & (RR - 1)) * 16).w;
         const int base = j0 & 31;
         const int rel = (lane - base) & 31;
-        const int need_c_cur = need_c;
-        if (u + 1 < NP) { rs_next = p.panel_row[pan0 + u + 2] - r0; need_c = p.panel_need[pan0 + u + 1]; }
-        trace_ev(p, lane, 8, 0, u);
-        wait_progress<NA, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c_cur, lane);
-        trace_ev(p, lane, 8, 1, u);
 
         // fold what the bulk warps prepared for this panel's columns
         T bsum = T(0);
@@ -331,11 +338,11 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
         }
         T Xown = T(0);
 #pragma unroll
-        for (int h = 0; h < PMAX; h += 8) {
+        for (int h = 0; h < PMAX; h += 4) {
             if (h < nrows) {
-                T w0[8], w1[8];
+                T w0[4], w1[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
                     const uint32_t wr = a_wwin + (uint32_t)((((j0 + h + i) & (RR - 1)) * WW + k0) * sizeof(T));
                     w0[i] = T(0); w1[i] = T(0);
@@ -343,7 +350,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
                     if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_t(wr + 32 * sizeof(T), T());
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     if (h + i < nrows) {
                         T en, d;
                         bool skip;

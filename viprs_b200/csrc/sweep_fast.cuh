@@ -19,6 +19,23 @@ namespace vb {
 
 constexpr int NAW = 4;                    // A warps
 constexpr int NCW = 4;                    // C warps
+// 11 warps per CTA.  Warps are dealt to the four SM sub-partitions round-robin (warp % 4), so warps 1, 5, 9 share
+// one scheduler: the latency-critical chain warp (1) and the producer (5) get it to themselves (9 exits at once);
+// the eight bulk warps run on the other three schedulers and cannot steal the chain's issue slots or pipes.
+#ifndef VB_FAST_ISOLATE
+#define VB_FAST_ISOLATE 0       // measured on B200 (C2 workload): 1.103 ms shared vs 1.135 ms isolated
+#endif
+#if VB_FAST_ISOLATE
+constexpr int FAST_WARPS = 11;
+constexpr int FAST_CHAIN_WARP = 1, FAST_PRODUCER_WARP = 5, FAST_IDLE_WARP = 9;
+__device__ __forceinline__ int fast_a_index(int warp) { return warp == 0 ? 0 : (warp >= 2 && warp <= 4) ? warp - 1 : -1; }
+__device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 6 && warp <= 8) ? warp - 6 : warp == 10 ? 3 : -1; }
+#else
+constexpr int FAST_WARPS = 10;
+constexpr int FAST_CHAIN_WARP = 9, FAST_PRODUCER_WARP = 8, FAST_IDLE_WARP = -1;
+__device__ __forceinline__ int fast_a_index(int warp) { return warp < 4 ? warp : -1; }
+__device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && warp < 8) ? warp - 4 : -1; }
+#endif
 constexpr int GT = 128;                   // threads per bulk group
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
@@ -54,14 +71,13 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // 
 }
 
 template <typename U, typename Model, int NLIMB>
-__global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
+__global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
                                                                               const typename Model::Args ma,
                                                                               const StateArgs<float> sa) {
     using T = float;
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int NVT = 32 / EPV;                        // LD vectors per thread per row
     constexpr bool DP4A = std::is_same<U, int8_t>::value;
-    static_assert(NAW + NCW == NBW, "the chain / producer warps sit behind NBW bulk warps");
     extern __shared__ __align__(128) unsigned char smem[];
 
     SmemView<T> sm;
@@ -86,6 +102,8 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
     const uint32_t zaddr_code = sbase + FL.zero + 16;    // code 0: contributes nothing to a decoded dot / axpy
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
+    const int ai = fast_a_index(warp), ci = fast_c_index(warp);
+    const int ta = ai * WARP + lane;                     // 0..127 inside the A group (when ai >= 0)
     const int blk = p.blk_order[blockIdx.x];
     const int r0 = p.blk_row[blk], r1 = p.blk_row[blk + 1];
     const int B = r1 - r0;
@@ -115,15 +133,15 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         if (lane == 0) red[warp] = mx;
         __syncthreads();
         mx = 0.f;
-        for (int w = 0; w < NBW + 2; ++w) mx = fmaxf(mx, red[w]);
+        for (int w = 0; w < FAST_WARPS; ++w) mx = fmaxf(mx, red[w]);
         int ex = 0;
         if (mx > 0.f) frexpf(mx, &ex);                   // mx = m * 2^ex, m in [0.5, 1): block scale 2^ex > max |eta_old|
         const float qs = ldexpf(1.f, 7 * NLIMB - 1 - ex);        // eta -> fixed point Q, |Q| <= 2^(7 NLIMB - 1); exact scaling
         wscale = ldexp(1.0, ex - (7 * NLIMB - 1));
-        if (tid < GT) {
+        if (ai >= 0) {
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
-                const int v = tid + GT * c;
+                const int v = ta + GT * c;
                 long long qsum = 0;
 #pragma unroll
                 for (int l = 0; l < NLIMB; ++l)
@@ -164,12 +182,12 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
             if (lane == 0) hc[0] = 0;
         }
     } else {
-        if (tid < GT) {
+        if (ai >= 0) {
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    const int col = (tid + GT * c) * EPV + e;
+                    const int col = (ta + GT * c) * EPV + e;
                     es[c][e] = (col < B) ? sa.eta[r0 + col] : 0.f;
                 }
             }
@@ -177,15 +195,16 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
     }
     __syncthreads();
 
-    if (warp == NBW) {
+    if (warp == FAST_IDLE_WARP) return;
+    if (warp == FAST_PRODUCER_WARP) {
         producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane);
-    } else if (warp == NBW + 1) {
+    } else if (warp == FAST_CHAIN_WARP) {
         chain_role<T, Model, NAW, NCW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
-    } else if (warp < NAW) {
+    } else if (ai >= 0) {
         // =============================== A: backward dots =====================================
         // Branch-free inner loop: a (row, vector) pair outside the row's range reads a 16-byte zero vector.
-        const int wa = warp;
-        const int t = tid;                                   // 0..127
+        const int wa = ai;
+        const int t = ta;                                    // 0..127
         const uint32_t zaddr = DP4A ? zaddr_raw : zaddr_code;
         int s = 0, k = 0;
         for (int u = 0; u < NP; ++u) {
@@ -195,6 +214,9 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
             const int4 pm = sm.panelmeta[s];
             const int P = pm.x, jl0 = pm.w;
             for (int r = wa; r < P; r += NAW) window_row<T, U>(smem, sm.rowmeta, sm.wwin, jl0 + r, lane);
+            [[maybe_unused]] int dig[DP4A ? NLIMB : 1];       // lane r: digit totals of row r of the panel
+#pragma unroll
+            for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) dig[l] = 0;
 #pragma unroll 1
             for (int rg = 0; rg < P; rg += 4) {
                 const int nv = min(4, P - rg);
@@ -248,24 +270,14 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
                     }
                 }
                 if constexpr (DP4A) {
-                    // exact integer totals: REDUX per (row, digit), digits recombined in int64.
-                    // sum_b u8 * digit = sum code * digit + 128 * sum digit over the row's packed range; the range
-                    // term (128 * sum of Q over the range, from the prefix array) is removed once per row, by warp 0.
-                    long long V[4];
+                    // exact integer totals: one REDUX per (row, digit); lane (rg + r) keeps the digits of row rg + r
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        long long x = 0;
 #pragma unroll
-                        for (int l = 0; l < NLIMB; ++l) x = x * 128 + (long long)__reduce_add_sync(0xffffffffu, acc[r][l]);
-                        V[r] = x;
-                    }
-                    if (lane < nv) {
-                        long long x = lane == 0 ? V[0] : lane == 1 ? V[1] : lane == 2 ? V[2] : V[3];
-                        if (wa == 0) {
-                            const int4 m = sm.rowmeta[(jl0 + rg + lane) & (RR - 1)];
-                            x -= 128 * (hc[min(m.z, HP - 1)] - hc[min(m.y, HP - 1)]);
+                        for (int l = 0; l < NLIMB; ++l) {
+                            const int tot = __reduce_add_sync(0xffffffffu, acc[r][l]);
+                            if (lane == rg + r) dig[l] = tot;
                         }
-                        sm.partial[wa * RR + ((jl0 + rg + lane) & (RR - 1))] = (float)((double)x * wscale);
                     }
                 } else {
                     T acc1[4];
@@ -275,6 +287,21 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
                     if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc1[0];
                 }
             }
+            if constexpr (DP4A) {
+                // lane r < P: recombine the digits of row r in int64.  sum_b u8 * digit = sum code * digit +
+                // 128 * sum digit over the row's packed range; the range term (128 * sum of Q over the range, from
+                // the prefix array) is removed once per row, by A warp 0.
+                if (lane < P) {
+                    long long x = 0;
+#pragma unroll
+                    for (int l = 0; l < NLIMB; ++l) x = x * 128 + (long long)dig[l];
+                    if (wa == 0) {
+                        const int4 m = sm.rowmeta[(jl0 + lane) & (RR - 1)];
+                        x -= 128 * (hc[min(m.z, HP - 1)] - hc[min(m.y, HP - 1)]);
+                    }
+                    sm.partial[wa * RR + ((jl0 + lane) & (RR - 1))] = (float)((double)x * wscale);
+                }
+            }
             __syncwarp();
             if (lane == 0) st_release(&sm.prog[wa], (uint32_t)(u + 1));
             trace_ev(p, lane, wa, 2, u);
@@ -282,8 +309,8 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         }
     } else {
         // =============================== C: forward axpy ======================================
-        const int wc = warp - NAW;
-        const int t = tid - GT;                              // 0..127
+        const int wc = ci;
+        const int t = ci * WARP + lane;                      // 0..127
         float f[NVT][EPV];
 #pragma unroll
         for (int c = 0; c < NVT; ++c)
@@ -293,7 +320,7 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
         int s = 0, k = 0;
         for (int v = 0; v < NP; ++v) {
             mbar_wait(&sm.cdone[s], k & 1);
-            trace_ev(p, lane, NAW + wc, 4, v);
+            trace_ev(p, lane, 4 + wc, 4, v);
             const int4 pm = sm.panelmeta[s];
             const int Pc = pm.x, jl0 = pm.w;
 #pragma unroll 1
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__((NAW + NCW + 2) * WARP, 2) sweep_fast_kernel(c
                 st_release(&sm.prog[NAW + wc], (uint32_t)(v + 1));
                 mbar_arrive(&sm.empty[s]);
             }
-            trace_ev(p, lane, NAW + wc, 5, v);
+            trace_ev(p, lane, 4 + wc, 5, v);
             if (++s == NST) { s = 0; ++k; }
         }
     }
