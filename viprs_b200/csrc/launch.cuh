@@ -23,7 +23,7 @@ static int make_plan(const viprs_b200_ld* ld, int tsize, SweepPlan& p, RingGeome
     p.prow = ld->d_prow; p.pcs = ld->d_pcs; p.blk_row = ld->d_blk_row; p.blk_panel = ld->d_blk_panel;
     p.panel_row = ld->d_panel_row; p.blk_order = ld->d_blk_order; p.panel_need = ld->d_panel_need;
     p.n_blocks = ld->n_blocks; p.stage_bytes = ld->stage_bytes; p.nst = g.nst; p.bpad = state_pad(ld->max_block);
-    p.l2_ahead = env_int("VIPRS_B200_L2_AHEAD", 8);
+    p.l2_ahead = env_int("VIPRS_B200_L2_AHEAD", 0);
     p.trace = nullptr;
     p.L = make_layout(p.bpad, tsize, ld->stage_bytes, g.nst);
     return g.nst == 0 ? VIPRS_B200_EBLOCK_TOO_LARGE : VIPRS_B200_OK;
