@@ -139,6 +139,21 @@ int viprs_b200_e_step_mixture_f64(const viprs_b200_ld_t* ld, int32_t K, const do
                                   const double* log_null_pi, const double* u_logs, const double* sqrt_half_var_tau,
                                   const double* mu_mult, double dq_scale, int32_t materialize_q, void* stream);
 
+/* viprs_b200_e_step_grid_{f32,f64}: one sweep with the semantics of e_step_grid<T,U,I>(..., threads=1)
+ * followed by update_q_factor_matrix (e_step.hpp:555-647, 266-303); argument meaning of cpp_e_step_grid
+ * (e_step_cpp.pyx:161-177).  var_gamma, var_mu, eta, q, eta_diff, u_logs, half_var_tau, mu_mult are (M,G)
+ * COLUMN-MAJOR (index model*M + j); std_beta has M entries; active_model_idx is a DEVICE array of n_active
+ * column indices -- the other columns are not touched.  q is in/out exactly as in the reference (maintained
+ * incrementally across sweeps).  LD blocks of up to 4096 SNPs. */
+int viprs_b200_e_step_grid_f32(const viprs_b200_ld_t* ld, int32_t G, int32_t n_active,
+                               const int32_t* active_model_idx, const float* std_beta, float* var_gamma,
+                               float* var_mu, float* eta, float* q, float* eta_diff, const float* u_logs,
+                               const float* half_var_tau, const float* mu_mult, float dq_scale, void* stream);
+int viprs_b200_e_step_grid_f64(const viprs_b200_ld_t* ld, int32_t G, int32_t n_active,
+                               const int32_t* active_model_idx, const double* std_beta, double* var_gamma,
+                               double* var_mu, double* eta, double* q, double* eta_diff, const double* u_logs,
+                               const double* half_var_tau, const double* mu_mult, double dq_scale, void* stream);
+
 /* q[j] += dq_scale * sum_{k>j} R_jk x[k]  -- the reference's update_q_factor (e_step.hpp:307-338)
  * as a stand-alone streaming kernel (x = eta for materialisation, or any vector). */
 int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float* q,
@@ -166,6 +181,15 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
                                   void* eta, void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
                                   const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
                                   int32_t threads, int32_t low_memory);
+
+/* cpp_e_step_grid(...) (e_step_cpp.pyx:161-195) with host buffers; (M,G) arrays Fortran-order, active_model_idx
+ * a host array of n_active column indices.  q is in/out. */
+int viprs_b200_cpp_e_step_grid(int32_t M, int32_t G, int32_t n_active, const int32_t* active_model_idx,
+                               const int32_t* ld_left_bound, const void* ld_indptr, int32_t indptr_is_i64,
+                               const void* ld_data, int32_t ld_dtype, int32_t float_dtype, const void* std_beta,
+                               void* var_gamma, void* var_mu, void* eta, void* q, void* eta_diff, const void* u_logs,
+                               const void* half_var_tau, const void* mu_mult, double dq_scale, int32_t threads,
+                               int32_t low_memory);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+timeout 600 python -m pytest tests/test_grid_gpu.py -m gpu -x -q 2>&1 | tail -30

@@ -44,10 +44,13 @@ SIGNATURES = {
     "viprs_b200_e_step_f64": (ctypes.c_int, [_vp] * 10 + [_f64, _i32, _vp]),
     "viprs_b200_e_step_mixture_f32": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f32, _i32, _vp]),
     "viprs_b200_e_step_mixture_f64": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f64, _i32, _vp]),
+    "viprs_b200_e_step_grid_f32": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f32, _vp]),
+    "viprs_b200_e_step_grid_f64": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f64, _vp]),
     "viprs_b200_backward_dot_f32": (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp]),
     "viprs_b200_backward_dot_f64": (ctypes.c_int, [_vp, _vp, _vp, _f64, _vp]),
     "viprs_b200_cpp_e_step": (ctypes.c_int, [_i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
     "viprs_b200_cpp_e_step_mixture": (ctypes.c_int, [_i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 10 + [_f64, _i32, _i32]),
+    "viprs_b200_cpp_e_step_grid": (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
 }
 
 

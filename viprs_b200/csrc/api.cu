@@ -107,3 +107,57 @@ extern "C" int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t
     return host_dropin(M, K, ld_left_bound, ld_indptr, indptr_is_i64, ld_data, ld_dtype, float_dtype, std_beta,
                        var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs, sqrt_half_var_tau, mu_mult, dq_scale);
 }
+
+// cpp_e_step_grid (e_step_cpp.pyx:161-195)
+extern "C" int viprs_b200_cpp_e_step_grid(int32_t M, int32_t G, int32_t n_active, const int32_t* active_model_idx,
+                                          const int32_t* ld_left_bound, const void* ld_indptr, int32_t indptr_is_i64,
+                                          const void* ld_data, int32_t ld_dtype, int32_t float_dtype,
+                                          const void* std_beta, void* var_gamma, void* var_mu, void* eta, void* q,
+                                          void* eta_diff, const void* u_logs, const void* half_var_tau,
+                                          const void* mu_mult, double dq_scale, int32_t threads, int32_t low_memory) {
+    (void)threads; (void)low_memory;
+    if (float_dtype != VIPRS_B200_F32 && float_dtype != VIPRS_B200_F64) return VIPRS_B200_EINVAL;
+    if (G < 1 || n_active < 0 || n_active > G || (n_active > 0 && !active_model_idx)) return VIPRS_B200_EINVAL;
+    if (!std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !half_var_tau || !mu_mult)
+        return VIPRS_B200_EINVAL;
+    viprs_b200_ld_t* ld = nullptr;
+    int rc = viprs_b200_ld_create(&ld, M, ld_left_bound, ld_indptr, indptr_is_i64, ld_data, ld_dtype,
+                                  VIPRS_B200_MEM_HOST, 0, nullptr);
+    if (rc) return rc;
+    const size_t ts = float_dtype == VIPRS_B200_F32 ? 4 : 8;
+    const size_t n1 = (size_t)M * ts, ng = n1 * (size_t)G, na = ((size_t)(n_active > 0 ? n_active : 1) * 4 + 15) & ~(size_t)15;
+    // layout: [gamma][mu][eta][q][diff][ulogs][hvt][mm] (ng each) [beta n1] [active]
+    DevBuf buf;
+    cudaError_t e = cudaMalloc(&buf.d, 8 * ng + n1 + 16 + na);
+    if (e != cudaSuccess) { viprs_b200_ld_destroy(ld); return (int)e; }
+    unsigned char* d = buf.d;
+    unsigned char *d_g = d, *d_mu = d + ng, *d_eta = d + 2 * ng, *d_q = d + 3 * ng, *d_diff = d + 4 * ng,
+                  *d_ul = d + 5 * ng, *d_hv = d + 6 * ng, *d_mm = d + 7 * ng, *d_beta = d + 8 * ng,
+                  *d_act = d + 8 * ng + ((n1 + 15) & ~(size_t)15);
+    auto up = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && n > 0) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, 0);
+    };
+    up(d_g, var_gamma, ng); up(d_mu, var_mu, ng); up(d_eta, eta, ng); up(d_q, q, ng); up(d_diff, eta_diff, ng);
+    up(d_ul, u_logs, ng); up(d_hv, half_var_tau, ng); up(d_mm, mu_mult, ng); up(d_beta, std_beta, n1);
+    up(d_act, active_model_idx, (size_t)n_active * 4);
+    if (e == cudaSuccess) {
+        if (ts == 4) {
+            using F = float;
+            rc = viprs_b200_e_step_grid_f32(ld, G, n_active, (const int32_t*)d_act, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta,
+                                            (F*)d_q, (F*)d_diff, (F*)d_ul, (F*)d_hv, (F*)d_mm, (F)dq_scale, nullptr);
+        } else {
+            using F = double;
+            rc = viprs_b200_e_step_grid_f64(ld, G, n_active, (const int32_t*)d_act, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta,
+                                            (F*)d_q, (F*)d_diff, (F*)d_ul, (F*)d_hv, (F*)d_mm, (F)dq_scale, nullptr);
+        }
+    }
+    auto down = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, 0);
+    };
+    down(var_gamma, d_g, ng); down(var_mu, d_mu, ng); down(eta, d_eta, ng); down(q, d_q, ng); down(eta_diff, d_diff, ng);
+    cudaError_t e2 = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = e2;
+    viprs_b200_ld_destroy(ld);
+    if (rc) return rc;
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}

@@ -1,0 +1,500 @@
+// viprs_b200 -- the grid sweep: e_step_grid<T,U,I> + update_q_factor_matrix<T,U,I> of the reference
+// (/root/reference/viprs/model/vi/e_step.hpp:555-647 and 266-303), threads=1 order, for sm_100a.
+//
+// One CTA owns one (LD block, tile of GT active grid columns) pair and walks the block's SNPs in order.  The LD
+// row is read once per CTA and shared by the GT columns of the tile (and, through L2, by the other tiles of the
+// same block, which are adjacent in blockIdx).
+//
+// q is kept the way the reference keeps it -- in/out and incremental -- but against the DENSE SYMMETRIC copy
+// of the block (zero diagonal), so that ONE full-row axpy per updated SNP
+//        q[k, g] = fma(R_jk, dq * eta_diff[j, g], q[k, g])      for every k of the block
+// replaces both the reference's upper-row axpy (:623) and its second pass over the matrix (:291-302).
+//
+// Warp roles (no __syncthreads after the prologue):
+//   warps 0..nbw-1  bulk : thread t owns GKPT = 16 columns x GT grid columns of q in REGISTERS for the whole
+//                      sweep (128 registers).  Per LD row: one 128-bit shared load of its 16 codes (int8), the GT
+//                      scaled deltas from a shared ring (broadcast loads), decode, 64 FFMA2 (or 64 DFMA).
+//                      After every panel the owner of the columns two panels ahead publishes them for the chain.
+//   aux warp 0      producer : 1-D TMA bulk copies of (16 rows x <= 4 KB) stages into an nst-deep ring.
+//   aux warp 1      chain : lane = (grid column g, slot w).  Per 16-row panel it holds X[c,g] = published q + the
+//                      not-yet-published corrections of the previous and the current panel for the 16/NW columns it
+//                      owns, runs the scalar update of GT columns at once, broadcasts dq*eta_diff with one SHFL per
+//                      step, and keeps a decoded 16 x 32 window of LD coefficients in shared memory.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int GP = 16;            // rows per panel
+constexpr int GCW = 4096;         // bytes of one row inside a ring stage (column chunk)
+constexpr int GKPT = 16;          // q columns per bulk thread
+constexpr int GNST_MAX = 4;       // ring depth
+constexpr int GAR = 4;            // depth (panels) of the delta ring
+constexpr int GWW = 32;           // decoded window width: the panel's own 16 columns + the next 16
+constexpr int GRID_MAX_BLOCK = 4096;   // 256 bulk threads x 16 columns
+constexpr int GRID_MAX_BW = 8;
+// Warps come in groups of four (one per SM sub-partition, each with its own 16K-register file).  The bulk warps
+// fill whole warpgroups; the last warpgroup holds the producer, the chain warp and two idle warps.  With three
+// warps per sub-partition ptxas may only assume 168 registers per thread, so the roles re-split the CTA's register
+// pool with setmaxnreg: bulk warpgroups 200 (128 of them are the q tile), the auxiliary warpgroup 96.
+constexpr int GRID_MAX_THREADS = (GRID_MAX_BW + 4) * WARP;
+constexpr int GRID_BULK_REGS = 200;
+constexpr int GRID_AUX_REGS = 96;
+inline int grid_threads(int nbw) { return (((nbw + 3) / 4) * 4 + 4) * WARP; }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <typename T> struct GridT;
+template <> struct GridT<float>  { static constexpr int GT = 8; };
+template <> struct GridT<double> { static constexpr int GT = 4; };
+
+struct GridLayout { uint32_t stages, wwin, wraw, pbuf, alpha, qpub, bars, prog, total; };
+inline GridLayout make_grid_layout(int tsize, int gt, int stage_bytes, int nst) {
+    GridLayout L;
+    uint32_t o = 0;
+    L.stages = o; o += (uint32_t)nst * (uint32_t)stage_bytes; o = (o + 127u) & ~127u;
+    L.wwin = o;   o += 2u * GP * GWW * (uint32_t)tsize;
+    L.wraw = o;   o += (uint32_t)GP * GWW * 8u;                       // raw window, sized for 8-byte LD elements
+    L.pbuf = o;   o += 2u * 5u * GP * (uint32_t)gt * (uint32_t)tsize;
+    L.alpha = o;  o += (uint32_t)GAR * GP * (uint32_t)gt * 8u;
+    L.qpub = o;   o += 2u * GP * (uint32_t)gt * (uint32_t)tsize;
+    L.bars = o;   o += (2u * GNST_MAX + GAR) * 8u;
+    L.prog = o;   o += GRID_MAX_BW * 4u;
+    L.total = o;
+    return L;
+}
+
+struct GridPlan {
+    const unsigned char* dense;    // dense symmetric blocks (biased integer codes), see ld.cu
+    const int64_t* dblk_off;       // [n_blocks] byte offset of every block
+    const int32_t* blk_row;        // [n_blocks+1]
+    const int32_t* blk_order;      // [n_blocks] most expensive first
+    const int32_t* active;         // [n_active] grid columns still iterating (e_step.hpp:606-609)
+    int n_active, n_tiles, M, nst, stage_bytes, nbw;
+    GridLayout L;
+};
+
+template <typename T>
+struct GridArgs {
+    const T* std_beta; T* var_gamma; T* var_mu; T* eta; T* q; T* eta_diff;
+    const T* u_logs; const T* half_var_tau; const T* mu_mult; T dq;
+};
+
+// decode one 16-byte LD vector into EPV values of the state type
+template <typename T, typename U> struct GridDecode;
+template <> struct GridDecode<float, int8_t> {
+    static __device__ __forceinline__ void vec(const uint4& c, float* o) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 p0, p1;
+            VecOps<float, int8_t>::pairs(w[i], p0, p1);
+            o[4 * i] = p0.x; o[4 * i + 1] = p0.y; o[4 * i + 2] = p1.x; o[4 * i + 3] = p1.y;
+        }
+    }
+};
+template <> struct GridDecode<float, int16_t> {
+    static __device__ __forceinline__ void vec(const uint4& c, float* o) {
+        const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 p = VecOps<float, int16_t>::pair(w[i]);
+            o[2 * i] = p.x; o[2 * i + 1] = p.y;
+        }
+    }
+};
+template <> struct GridDecode<float, float> {
+    static __device__ __forceinline__ void vec(const uint4& c, float* o) {
+        o[0] = __uint_as_float(c.x); o[1] = __uint_as_float(c.y); o[2] = __uint_as_float(c.z); o[3] = __uint_as_float(c.w);
+    }
+};
+template <typename U> struct GridDecode<double, U> {
+    static __device__ __forceinline__ void vec(const uint4& c, double* o) { DecodeD<U>::vec(c, o); }
+};
+
+// cp.async (LDGSTS): global -> shared without a register round trip; N = 4, 8 or 16 bytes
+template <int N>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+    if constexpr (N == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T, typename U>
+__global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const GridPlan p, const GridArgs<T> a) {
+    constexpr int GT = GridT<T>::GT;
+    constexpr int NW = WARP / GT;                 // chain lanes per grid column
+    constexpr int RPL = GP / NW;                  // panel rows (= columns) per chain lane
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+    constexpr int NVT = GKPT / EPV;               // LD vectors per bulk thread per row
+    constexpr bool F32 = std::is_same<T, float>::value;
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
+    const int nbw = p.nbw, NT = nbw * WARP, NST = p.nst;
+    const int blk = p.blk_order[blockIdx.x / p.n_tiles];
+    const int tile = blockIdx.x % p.n_tiles;
+    const int r0 = p.blk_row[blk];
+    const int B = p.blk_row[blk + 1] - r0;
+    const int Bp = (B + 15) & ~15;
+    const int row_bytes = Bp * ES;
+    const int NP = (B + GP - 1) / GP;
+    const int nck = (row_bytes + GCW - 1) / GCW;
+    const unsigned char* gblk = p.dense + p.dblk_off[blk];
+    const size_t M = (size_t)p.M;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.L.bars);
+    uint64_t* empty = full + GNST_MAX;
+    uint64_t* cdone = full + 2 * GNST_MAX;
+    uint32_t* prog = reinterpret_cast<uint32_t*>(smem + p.L.prog);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_alpha = sbase + p.L.alpha, a_qpub = sbase + p.L.qpub, a_wwin = sbase + p.L.wwin;
+
+    if (tid == 0) {
+        for (int s = 0; s < GNST_MAX; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)nbw); }
+        for (int s = 0; s < GAR; ++s) mbar_init(&cdone[s], 1);
+        for (int w = 0; w < GRID_MAX_BW; ++w) prog[w] = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int aux0 = ((nbw + 3) / 4) * 4;          // first warp of the auxiliary warpgroup
+    // (each role's code must be dominated by its own setmaxnreg for ptxas to allocate against the new limit)
+    if (warp >= aux0) {
+      reg_dec<GRID_AUX_REGS>();
+      if (warp == aux0) {
+        // =============================== producer ============================================
+        int s = 0, k = 0;
+        for (int u = 0; u < NP; ++u) {
+            const int nrows = min(GP, B - u * GP);
+            for (int c = 0; c < nck; ++c) {
+                const int cb = min(GCW, row_bytes - c * GCW);
+                if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+                if (lane == 0) {
+                    unsigned char* dst = smem + p.L.stages + (size_t)s * p.stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(nrows * cb));
+                    if (nck == 1) {
+                        tma_load_1d(dst, gblk + (size_t)u * GP * row_bytes, (uint32_t)(nrows * cb), &full[s]);
+                    } else {
+                        for (int r = 0; r < nrows; ++r)
+                            tma_load_1d(dst + (size_t)r * cb, gblk + (size_t)(u * GP + r) * row_bytes + (size_t)c * GCW,
+                                        (uint32_t)cb, &full[s]);
+                    }
+                }
+                __syncwarp();
+                if (++s == NST) { s = 0; ++k; }
+            }
+        }
+      } else if (warp == aux0 + 1) {
+        // =============================== chain ===============================================
+        const int g = lane % GT, w = lane / GT;
+        const int gi = tile * GT + g;
+        const bool gvalid = gi < p.n_active;
+        const size_t colbase = (size_t)p.active[gvalid ? gi : tile * GT] * M + (size_t)r0;
+        const T dq = a.dq;
+        T mm[RPL], ul[RPL], hv[RPL], eo[RPL], bt[RPL];
+        T X[RPL], Y[RPL];
+#pragma unroll
+        for (int m = 0; m < RPL; ++m) { X[m] = T(0); Y[m] = T(0); }
+        // The per-(SNP, column) inputs of the next panel and the raw LD window of the next panel are staged through
+        // shared memory with cp.async (LDGSTS): no registers stay live across the panel.
+        //   pbuf[2][5][GP][GT] of T : mu_mult, u_logs, half_var_tau, eta, std_beta of the lane's own rows
+        //   wraw[GP][GWW] of U      : rows of the panel x columns [16u, 16u + 32)
+        const uint32_t a_pbuf = sbase + p.L.pbuf, a_wraw = sbase + p.L.wraw;
+        auto stage_params = [&](int u) {
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int cl = RPL * w + m, j = u * GP + cl;
+                if (j < B) {
+                    const size_t idx = colbase + (size_t)j;
+                    const uint32_t d = a_pbuf + (uint32_t)(((((u & 1) * 5) * GP + cl) * GT + g) * sizeof(T));
+                    cp_async<sizeof(T)>(d, a.mu_mult + idx);
+                    cp_async<sizeof(T)>(d + (uint32_t)(1 * GP * GT * sizeof(T)), a.u_logs + idx);
+                    cp_async<sizeof(T)>(d + (uint32_t)(2 * GP * GT * sizeof(T)), a.half_var_tau + idx);
+                    cp_async<sizeof(T)>(d + (uint32_t)(3 * GP * GT * sizeof(T)), a.eta + idx);
+                    cp_async<sizeof(T)>(d + (uint32_t)(4 * GP * GT * sizeof(T)), a.std_beta + r0 + j);
+                }
+            }
+        };
+        auto fetch_params = [&](int u) {
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int cl = RPL * w + m;
+                const bool ok = u * GP + cl < B;
+                const uint32_t d = a_pbuf + (uint32_t)(((((u & 1) * 5) * GP + cl) * GT + g) * sizeof(T));
+                mm[m] = ok ? lds_t(d, T()) : T(0);
+                ul[m] = ok ? lds_t(d + (uint32_t)(1 * GP * GT * sizeof(T)), T()) : T(0);
+                hv[m] = ok ? lds_t(d + (uint32_t)(2 * GP * GT * sizeof(T)), T()) : T(0);
+                eo[m] = ok ? lds_t(d + (uint32_t)(3 * GP * GT * sizeof(T)), T()) : T(0);
+                bt[m] = ok ? lds_t(d + (uint32_t)(4 * GP * GT * sizeof(T)), T()) : T(0);
+            }
+        };
+        // lane l stages / decodes row l/2, half l%2 (16 elements) of the window
+        const int wr = lane >> 1, wh = lane & 1;
+        auto stage_window = [&](int u) -> bool {
+            const int row = u * GP + wr, col = u * GP + 16 * wh;
+            const bool ok = (row < B) && (col + 16 <= Bp);
+            if (ok) {
+                const unsigned char* src = gblk + (size_t)row * row_bytes + (size_t)col * ES;
+#pragma unroll
+                for (int c = 0; c < ES; ++c) cp_async<16>(a_wraw + (uint32_t)((wr * GWW + 16 * wh) * ES + 16 * c), src + 16 * c);
+            }
+            return ok;
+        };
+        auto decode_window = [&](int u, bool ok) {
+            const uint32_t dst = a_wwin + (uint32_t)((((u & 1) * GP + wr) * GWW + 16 * wh) * sizeof(T));
+#pragma unroll
+            for (int c = 0; c < ES; ++c) {
+                T v[EPV];
+                if (ok) {
+                    const uint4 rv = lds128(a_wraw + (uint32_t)((wr * GWW + 16 * wh) * ES + 16 * c));
+                    GridDecode<T, U>::vec(rv, v);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) v[e] = T(0);
+                }
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) sts_t(dst + (uint32_t)((c * EPV + e) * sizeof(T)), v[e]);
+            }
+        };
+
+        stage_params(0);
+        bool wok = stage_window(0);
+        cp_async_wait_all();
+        decode_window(0, wok);
+        fetch_params(0);
+        __syncwarp();
+
+        for (int u = 0; u < NP; ++u) {
+            const int j0 = u * GP;
+            const int nrows = min(GP, B - j0);
+            if (u + 1 < NP) { stage_params(u + 1); wok = stage_window(u + 1); }
+            // every bulk warp has applied (and published past) panel u-2
+            if (u >= 2) {
+                uint32_t spins = 0;
+                for (;;) {
+                    const bool ok = (lane >= nbw) || (ld_acquire(prog + lane) >= (uint32_t)(u - 1));
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > kSpinLimit) __trap();
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int cl = RPL * w + m;
+                T base;
+                if (u >= 2) base = lds_t(a_qpub + (uint32_t)((((u & 1) * GP + cl) * GT + g) * sizeof(T)), T());
+                else base = (j0 + cl < B) ? a.q[colbase + (size_t)(j0 + cl)] : T(0);
+                X[m] = add_t(base, Y[m]);
+                Y[m] = T(0);
+            }
+            const uint32_t wrow = a_wwin + (uint32_t)(((u & 1) * GP * GWW + RPL * w) * sizeof(T));
+            const uint32_t arow = a_alpha + (uint32_t)(((u % GAR) * GP * GT + g) * 8);
+#pragma unroll 1
+            for (int ow = 0; ow < NW; ++ow) {            // the NW lanes of a grid column take turns: RPL rows each
+                if (ow * RPL >= nrows) break;
+                const bool own = (w == ow);
+                const int src_lane = g + GT * ow;
+#pragma unroll
+                for (int m = 0; m < RPL; ++m) {
+                    const int i = ow * RPL + m;
+                    if (i < nrows) {
+                        T cX[RPL], cY[RPL];            // RPL * sizeof(T) == 16: one 128-bit load each
+                        {
+                            const uint4 vx = lds128(wrow + (uint32_t)(i * GWW * sizeof(T)));
+                            const uint4 vy = lds128(wrow + (uint32_t)((i * GWW + 16) * sizeof(T)));
+                            memcpy(cX, &vx, 16);
+                            memcpy(cY, &vy, 16);
+                        }
+                        const T mu = mul_t(mm[m], add_t(bt[m], -X[m]));                      // :613
+                        const T gam = sigmoid_t(add_t(ul[m], mul_t(mul_t(hv[m], mu), mu)));  // :616-617
+                        const T d = add_t(mul_t(gam, mu), -eo[m]);                           // :620
+                        const T al = mul_t(dq, d);                                           // :623 dq_scale*eta_diff
+                        if (own) {
+                            const T av = gvalid ? al : T(0);
+                            if constexpr (F32) {
+                                asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(arow + (uint32_t)(i * GT * 8)), "f"(av) : "memory");
+                            } else {
+                                sts_t(arow + (uint32_t)(i * GT * 8), av);
+                            }
+                            if (gvalid) {
+                                const size_t idx = colbase + (size_t)(j0 + i);
+                                a.var_mu[idx] = mu; a.var_gamma[idx] = gam; a.eta_diff[idx] = d;
+                                a.eta[idx] = add_t(eo[m], d);                                // :633
+                            }
+                        }
+                        const T ab = shfl_t(al, src_lane);
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) {
+                            X[t] = fma_t(cX[t], ab, X[t]);
+                            Y[t] = fma_t(cY[t], ab, Y[t]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cdone[u % GAR]);
+            if (u + 1 < NP) {
+                cp_async_wait_all();
+                decode_window(u + 1, wok);
+                fetch_params(u + 1);
+            }
+            __syncwarp();
+        }
+      }
+    } else {
+        reg_inc<GRID_BULK_REGS>();
+        if (warp >= nbw) return;                   // padding warps of the last bulk warpgroup
+        // =============================== bulk ================================================
+        const int t = tid;                                      // 0 .. NT-1
+        int gcol[GT];
+        bool gval[GT];
+#pragma unroll
+        for (int g = 0; g < GT; ++g) {
+            const int gi = tile * GT + g;
+            gval[g] = gi < p.n_active;
+            gcol[g] = p.active[gval[g] ? gi : tile * GT];
+        }
+        // q registers: float -> pairs of adjacent columns (FFMA2 along the column pair), double -> scalars
+        using QT = typename std::conditional<F32, float2, double>::type;
+        constexpr int QE = F32 ? EPV / 2 : EPV;
+        QT qr[NVT][QE][GT];
+#pragma unroll
+        for (int i = 0; i < NVT; ++i) {
+            const int col0 = (t + NT * i) * EPV;
+#pragma unroll
+            for (int e = 0; e < QE; ++e) {
+#pragma unroll
+                for (int g = 0; g < GT; ++g) {
+                    const size_t cb = (size_t)gcol[g] * M + (size_t)r0;
+                    if constexpr (F32) {
+                        const int c0 = col0 + 2 * e;
+                        qr[i][e][g].x = (c0 < B && gval[g]) ? a.q[cb + c0] : 0.f;
+                        qr[i][e][g].y = (c0 + 1 < B && gval[g]) ? a.q[cb + c0 + 1] : 0.f;
+                    } else {
+                        const int c0 = col0 + e;
+                        qr[i][e][g] = (c0 < B && gval[g]) ? a.q[cb + c0] : 0.0;
+                    }
+                }
+            }
+        }
+        uint32_t voff[NVT];      // byte offset of vector i inside its chunk's stage row
+        int vchunk[NVT];         // chunk index, or -1 when the vector lies beyond the block's padded width
+#pragma unroll
+        for (int i = 0; i < NVT; ++i) {
+            const int byte = 16 * (t + NT * i);
+            const int ck = (nck == 1) ? 0 : ((NT * i) >> 8);       // chunk of vector i = floor(16 (t + NT i) / GCW)
+            vchunk[i] = (byte < row_bytes) ? ck : -1;
+            voff[i] = (uint32_t)(byte - ck * GCW);
+        }
+
+        int s = 0, k = 0;
+        for (int u = 0; u < NP; ++u) {
+            const int nrows = min(GP, B - u * GP);
+            mbar_wait(&cdone[u % GAR], (u / GAR) & 1);
+            const uint32_t abase = a_alpha + (uint32_t)((u % GAR) * GP * GT * 8);
+            for (int c = 0; c < nck; ++c) {
+                const int cb = min(GCW, row_bytes - c * GCW);
+                mbar_wait(&full[s], k & 1);
+                const uint32_t st = sbase + p.L.stages + (uint32_t)s * (uint32_t)p.stage_bytes;
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < NVT; ++i) any |= (vchunk[i] == c);
+                if (any) {
+#pragma unroll 2
+                    for (int r = 0; r < nrows; ++r) {
+                        // the GT scaled deltas of row r (float: stored duplicated, one float2 per grid column)
+                        QT al[GT];
+                        if constexpr (F32) {
+#pragma unroll
+                            for (int gg = 0; gg < GT; gg += 2) {
+                                const uint4 v = lds128(abase + (uint32_t)((r * GT + gg) * 8));
+                                al[gg] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+                                al[gg + 1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+                            }
+                        } else {
+#pragma unroll
+                            for (int gg = 0; gg < GT; gg += 2) {
+                                const uint4 v = lds128(abase + (uint32_t)((r * GT + gg) * 8));
+                                al[gg] = __hiloint2double((int)v.y, (int)v.x);
+                                al[gg + 1] = __hiloint2double((int)v.w, (int)v.z);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < NVT; ++i) {
+                            if (vchunk[i] == c) {
+                                const uint4 cv = lds128(st + (uint32_t)(r * cb) + voff[i]);
+                                T v[EPV];
+                                GridDecode<T, U>::vec(cv, v);
+#pragma unroll
+                                for (int e = 0; e < QE; ++e) {
+#pragma unroll
+                                    for (int g = 0; g < GT; ++g) {
+                                        if constexpr (F32) {
+                                            qr[i][e][g] = fma2(make_float2(v[2 * e], v[2 * e + 1]), al[g], qr[i][e][g]);
+                                        } else {
+                                            qr[i][e][g] = fma(v[e], al[g], qr[i][e][g]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == NST) { s = 0; ++k; }
+            }
+            // publish the columns of panel u+2 (complete through panel u) for the chain
+            const int pp = u + 2;
+            if (pp < NP) {
+#pragma unroll
+                for (int i = 0; i < NVT; ++i) {
+                    const int vv = t + NT * i;
+                    if (vv / NVT == pp) {
+                        const int kk = (vv % NVT) * EPV;
+#pragma unroll
+                        for (int e = 0; e < QE; ++e) {
+#pragma unroll
+                            for (int g = 0; g < GT; ++g) {
+                                if constexpr (F32) {
+                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + 2 * e) * GT + g) * 4), qr[i][e][g].x);
+                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + 2 * e + 1) * GT + g) * 4), qr[i][e][g].y);
+                                } else {
+                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + e) * GT + g) * 8), qr[i][e][g]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) st_release(&prog[warp], (uint32_t)(u + 1));
+        }
+        // ---- epilogue: q back to global memory ------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < NVT; ++i) {
+            const int col0 = (t + NT * i) * EPV;
+#pragma unroll
+            for (int e = 0; e < QE; ++e) {
+#pragma unroll
+                for (int g = 0; g < GT; ++g) {
+                    if (!gval[g]) continue;
+                    const size_t cb = (size_t)gcol[g] * M + (size_t)r0;
+                    if constexpr (F32) {
+                        const int c0 = col0 + 2 * e;
+                        if (c0 < B) a.q[cb + c0] = qr[i][e][g].x;
+                        if (c0 + 1 < B) a.q[cb + c0 + 1] = qr[i][e][g].y;
+                    } else {
+                        const int c0 = col0 + e;
+                        if (c0 < B) a.q[cb + c0] = qr[i][e][g];
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace vb

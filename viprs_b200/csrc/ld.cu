@@ -45,6 +45,34 @@ __global__ void pack_rows_kernel(int M, const U* __restrict__ src, const int64_t
     }
 }
 
+// dense symmetric copy of one LD block row: out[j][k] = R[min(j,k)][max(j,k)] (0 on the diagonal / outside the
+// stored run / in the padding), read from the packed upper-triangular rows.  One CTA per row.
+template <typename U>
+__global__ void mirror_dense_kernel(int n_blocks, const int32_t* __restrict__ blk_row, const int64_t* __restrict__ dblk_off,
+                                    const U* __restrict__ packed, const int64_t* __restrict__ prow,
+                                    const int32_t* __restrict__ pcs, unsigned char* __restrict__ dense) {
+    const int row = blockIdx.x;
+    int lo = 0, hi = n_blocks;                     // block of this row: blk_row[lo] <= row < blk_row[lo+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blk_row[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int r0 = blk_row[lo], B = blk_row[lo + 1] - r0, Bp = (B + 15) & ~15;
+    const int j = row - r0;
+    U* out = reinterpret_cast<U*>(dense + dblk_off[lo]) + (size_t)j * Bp;
+    const U zero = bias(U(0));
+    for (int k = threadIdx.x; k < Bp; k += blockDim.x) {
+        U v = zero;
+        if (k < B && k != j) {
+            const int a = min(j, k), b = max(j, k);
+            const int64_t p0 = prow[r0 + a];
+            const int64_t idx = (int64_t)(r0 + b) - pcs[r0 + a];
+            if (idx >= 0 && idx < prow[r0 + a + 1] - p0) v = packed[p0 + idx];
+        }
+        out[k] = v;
+    }
+}
+
 static int elem_size(int dt) {
     switch (dt) {
         case VIPRS_B200_I8: return 1;
@@ -346,8 +374,54 @@ fail:
     return rc;
 }
 
+int vb::ensure_dense(const viprs_b200_ld* h, cudaStream_t stream) {
+    if (h->d_dense) return VIPRS_B200_OK;
+    const int nb = h->n_blocks;
+    std::vector<int64_t> off(nb);
+    int64_t o = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int64_t B = h->h_blk_row[b + 1] - h->h_blk_row[b], Bp = (B + 15) & ~15LL;
+        off[b] = o;
+        o += (B * Bp * h->esize + 127) & ~127LL;
+    }
+    void* dd = nullptr;
+    int64_t* doff = nullptr;
+    cudaError_t e = cudaMalloc(&dd, (size_t)o + 1024);     // slack: the chain warp's window loads may run past a row
+    if (e == cudaSuccess) e = cudaMalloc(&doff, sizeof(int64_t) * nb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dd, 0, (size_t)o + 1024, stream);
+    if (e == cudaSuccess) {
+        dim3 grid(h->M), block(128);
+        unsigned char* d8 = reinterpret_cast<unsigned char*>(dd);
+        switch (h->ld_dtype) {
+            case VIPRS_B200_I8:
+                vb::mirror_dense_kernel<int8_t><<<grid, block, 0, stream>>>(nb, h->d_blk_row, doff, (const int8_t*)h->d_packed, h->d_prow, h->d_pcs, d8);
+                break;
+            case VIPRS_B200_I16:
+                vb::mirror_dense_kernel<int16_t><<<grid, block, 0, stream>>>(nb, h->d_blk_row, doff, (const int16_t*)h->d_packed, h->d_prow, h->d_pcs, d8);
+                break;
+            case VIPRS_B200_F32:
+                vb::mirror_dense_kernel<float><<<grid, block, 0, stream>>>(nb, h->d_blk_row, doff, (const float*)h->d_packed, h->d_prow, h->d_pcs, d8);
+                break;
+            default:
+                vb::mirror_dense_kernel<double><<<grid, block, 0, stream>>>(nb, h->d_blk_row, doff, (const double*)h->d_packed, h->d_prow, h->d_pcs, d8);
+                break;
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);       // `off` goes out of scope
+    if (e != cudaSuccess) {
+        cudaFree(dd); cudaFree(doff);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? VIPRS_B200_ENOMEM : (int)e;
+    }
+    h->d_dense = dd; h->d_dblk_off = doff; h->dense_bytes = o;
+    return VIPRS_B200_OK;
+}
+
 extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     if (!h) return VIPRS_B200_OK;
+    cudaFree(h->d_dense); cudaFree(h->d_dblk_off);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
     cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);
     delete h;

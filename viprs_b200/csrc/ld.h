@@ -32,6 +32,12 @@ struct viprs_b200_ld {
     int32_t* d_blk_order = nullptr;// [n_blocks] block ids, most expensive first (LPT schedule)
 
     std::vector<int32_t> h_blk_row;  // host copy for callers (sharding across GPUs)
+
+    // dense symmetric block layout for the grid sweep (built lazily by vb::ensure_dense): block b is a
+    // B_b x Bp_b row-major matrix (Bp_b = B_b rounded up to 16 elements), zero diagonal, biased integer codes
+    mutable void* d_dense = nullptr;
+    mutable int64_t* d_dblk_off = nullptr;   // [n_blocks] byte offset of every block (128-byte aligned)
+    mutable int64_t dense_bytes = 0;
 };
 
 namespace vb {
@@ -42,4 +48,6 @@ struct RingGeometry { int nst; int smem_bytes; int ctas_per_sm; };
 RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize);
 // same for the register-resident kernel (float32 state, blocks <= 4096 SNPs); nst == 0: not applicable
 RingGeometry fast_ring_geometry(const viprs_b200_ld* ld);
+// build the dense symmetric block layout if it does not exist yet; 0 or an error code
+int ensure_dense(const viprs_b200_ld* ld, cudaStream_t stream);
 }  // namespace vb

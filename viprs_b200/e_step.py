@@ -74,6 +74,76 @@ def e_step_mixture_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, log
     _lib.check(rc, "viprs_b200_e_step_mixture")
 
 
+def e_step_grid_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, half_var_tau, mu_mult, dq_scale,
+                       active_model_idx):
+    """
+    One grid sweep on a DeviceLD.  (M,G) arrays are COLUMN-MAJOR CUDA tensors -- i.e. torch tensors of shape
+    (G, M) that are C-contiguous, or any (M, G) tensor ``t`` with ``t.t().is_contiguous()``.  q is in/out.
+    ``active_model_idx``: int32 CUDA tensor of the columns to update.
+    """
+    L = _lib.lib()
+    dt = var_mu.dtype
+    mats = (var_gamma, var_mu, eta, q, eta_diff, u_logs, half_var_tau, mu_mult)
+
+    def colmajor(t):
+        if t.dim() != 2:
+            raise ValueError("e_step_grid_device: (M,G) arrays must be 2-D")
+        if t.shape[0] == ld.M and t.t().is_contiguous():
+            return t.shape[1]
+        raise ValueError("e_step_grid_device: (M,G) arrays must be column-major (Fortran order) with M rows")
+
+    G = colmajor(var_mu)
+    for t in mats:
+        if not (t.is_cuda and t.dtype == dt and colmajor(t) == G):
+            raise ValueError("e_step_grid_device: arrays must be CUDA tensors of one float dtype and one shape")
+    if not (std_beta.is_cuda and std_beta.dtype == dt and std_beta.is_contiguous() and std_beta.numel() == ld.M):
+        raise ValueError("e_step_grid_device: std_beta must be a contiguous CUDA tensor of length M")
+    act = active_model_idx
+    if not (act.is_cuda and act.dtype == torch.int32 and act.is_contiguous()):
+        raise ValueError("e_step_grid_device: active_model_idx must be a contiguous int32 CUDA tensor")
+    fn = L.viprs_b200_e_step_grid_f32 if dt == torch.float32 else L.viprs_b200_e_step_grid_f64
+    rc = fn(ld.handle, G, act.numel(), act.data_ptr(), std_beta.data_ptr(), *[t.data_ptr() for t in mats],
+            float(dq_scale), _stream_ptr())
+    _lib.check(rc, "viprs_b200_e_step_grid")
+
+
+def cpp_e_step_grid(ld_left_bound, ld_indptr, ld_data, std_beta, var_gamma, var_mu, eta, q, eta_diff,
+                    u_logs, half_var_tau, mu_mult, dq_scale, active_model_idx, threads=1, low_memory=True):
+    """
+    cpp_e_step_grid (e_step_cpp.pyx:161-195): (M,G) arrays Fortran-order, in-place outputs, only the columns in
+    ``active_model_idx`` are touched.  ``threads`` is accepted and ignored (always the sequential sweep).
+    """
+    if isinstance(ld_data, torch.Tensor):
+        ld = device_ld_for(ld_left_bound, ld_indptr, ld_data)
+        act = torch.as_tensor(active_model_idx, dtype=torch.int32, device=ld_data.device).contiguous()
+        return e_step_grid_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, half_var_tau, mu_mult,
+                                  dq_scale, act)
+    L = _lib.lib()
+    M, G = var_mu.shape
+    dt = var_mu.dtype
+    fdt = _FLOAT_DT[dt]
+    lb, ip, ld_data = _host_index_arrays(ld_left_bound, ld_indptr, ld_data)
+    act = np.ascontiguousarray(active_model_idx, dtype=np.int32)
+    if act.size and (act.min() < 0 or act.max() >= G):
+        raise ValueError("cpp_e_step_grid: active_model_idx out of range")
+    beta = np.ascontiguousarray(std_beta, dtype=dt)
+    ins = []
+    for a in (u_logs, half_var_tau, mu_mult):
+        a = np.asfortranarray(a, dtype=dt)
+        if a.shape != (M, G):
+            raise ValueError("cpp_e_step_grid: u_logs / half_var_tau / mu_mult must be (M, G)")
+        ins.append(a)
+    for a in (var_gamma, var_mu, eta, q, eta_diff):
+        if not (a.flags["F_CONTIGUOUS"] and a.dtype == dt and a.shape == (M, G)):
+            raise ValueError("cpp_e_step_grid: in/out arrays must be Fortran-contiguous (M, G) of one float dtype")
+    rc = L.viprs_b200_cpp_e_step_grid(M, G, act.shape[0], act.ctypes.data, lb.ctypes.data, ip.ctypes.data,
+                                      int(ip.dtype == np.int64), ld_data.ctypes.data, _NP_DT[ld_data.dtype], fdt,
+                                      beta.ctypes.data, var_gamma.ctypes.data, var_mu.ctypes.data, eta.ctypes.data,
+                                      q.ctypes.data, eta_diff.ctypes.data, ins[0].ctypes.data, ins[1].ctypes.data,
+                                      ins[2].ctypes.data, float(dq_scale), int(threads), int(bool(low_memory)))
+    _lib.check(rc, "viprs_b200_cpp_e_step_grid")
+
+
 def _host_index_arrays(ld_left_bound, ld_indptr, ld_data):
     lb = np.ascontiguousarray(ld_left_bound, dtype=np.int32)
     ip = np.ascontiguousarray(ld_indptr)
