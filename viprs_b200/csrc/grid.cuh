@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         const bool gvalid = gi < p.n_active;
         const size_t colbase = (size_t)p.active[gvalid ? gi : tile * GT] * M + (size_t)r0;
         const T dq = a.dq;
-        T mm[RPL], ul[RPL], hv[RPL], eo[RPL], bt[RPL];
+        T mm[RPL], ul[RPL], hm[RPL], eo[RPL], bt[RPL], ndqeo[RPL];
         T X[RPL], Y[RPL];
 #pragma unroll
         for (int m = 0; m < RPL; ++m) { X[m] = T(0); Y[m] = T(0); }
@@ -227,9 +227,10 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 const uint32_t d = a_pbuf + (uint32_t)(((((u & 1) * 5) * GP + cl) * GT + g) * sizeof(T));
                 mm[m] = ok ? lds_t(d, T()) : T(0);
                 ul[m] = ok ? lds_t(d + (uint32_t)(1 * GP * GT * sizeof(T)), T()) : T(0);
-                hv[m] = ok ? lds_t(d + (uint32_t)(2 * GP * GT * sizeof(T)), T()) : T(0);
+                hm[m] = ok ? mul_t(lds_t(d + (uint32_t)(2 * GP * GT * sizeof(T)), T()), mm[m]) : T(0);
                 eo[m] = ok ? lds_t(d + (uint32_t)(3 * GP * GT * sizeof(T)), T()) : T(0);
                 bt[m] = ok ? lds_t(d + (uint32_t)(4 * GP * GT * sizeof(T)), T()) : T(0);
+                ndqeo[m] = -mul_t(dq, eo[m]);
             }
         };
         // lane l stages / decodes row l/2, half l%2 (16 elements) of the window
@@ -270,7 +271,6 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
 
         for (int u = 0; u < NP; ++u) {
             const int j0 = u * GP;
-            const int nrows = min(GP, B - j0);
             if (u + 1 < NP) { stage_params(u + 1); wok = stage_window(u + 1); }
             // every bulk warp has applied (and published past) panel u-2
             if (u >= 2) {
@@ -291,47 +291,58 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 Y[m] = T(0);
             }
             const uint32_t wrow = a_wwin + (uint32_t)(((u & 1) * GP * GWW + RPL * w) * sizeof(T));
-            const uint32_t arow = a_alpha + (uint32_t)(((u % GAR) * GP * GT + g) * 8);
+            // The steps below are branch-free and store-free: rows past the block end carry all-zero inputs (their
+            // delta is exactly 0), outputs are kept by predicated moves and written once per panel.
+            T o_mu[RPL], o_g[RPL], o_al[RPL];
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) { o_mu[m] = T(0); o_g[m] = T(0); o_al[m] = T(0); }
 #pragma unroll 1
             for (int ow = 0; ow < NW; ++ow) {            // the NW lanes of a grid column take turns: RPL rows each
-                if (ow * RPL >= nrows) break;
                 const bool own = (w == ow);
                 const int src_lane = g + GT * ow;
+                uint4 vx[RPL], vy[RPL];                  // window coefficients of the RPL steps, fetched up front
 #pragma unroll
                 for (int m = 0; m < RPL; ++m) {
-                    const int i = ow * RPL + m;
-                    if (i < nrows) {
-                        T cX[RPL], cY[RPL];            // RPL * sizeof(T) == 16: one 128-bit load each
-                        {
-                            const uint4 vx = lds128(wrow + (uint32_t)(i * GWW * sizeof(T)));
-                            const uint4 vy = lds128(wrow + (uint32_t)((i * GWW + 16) * sizeof(T)));
-                            memcpy(cX, &vx, 16);
-                            memcpy(cY, &vy, 16);
-                        }
-                        const T mu = mul_t(mm[m], add_t(bt[m], -X[m]));                      // :613
-                        const T gam = sigmoid_t(add_t(ul[m], mul_t(mul_t(hv[m], mu), mu)));  // :616-617
-                        const T d = add_t(mul_t(gam, mu), -eo[m]);                           // :620
-                        const T al = mul_t(dq, d);                                           // :623 dq_scale*eta_diff
-                        if (own) {
-                            const T av = gvalid ? al : T(0);
-                            if constexpr (F32) {
-                                asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(arow + (uint32_t)(i * GT * 8)), "f"(av) : "memory");
-                            } else {
-                                sts_t(arow + (uint32_t)(i * GT * 8), av);
-                            }
-                            if (gvalid) {
-                                const size_t idx = colbase + (size_t)(j0 + i);
-                                a.var_mu[idx] = mu; a.var_gamma[idx] = gam; a.eta_diff[idx] = d;
-                                a.eta[idx] = add_t(eo[m], d);                                // :633
-                            }
-                        }
-                        const T ab = shfl_t(al, src_lane);
+                    vx[m] = lds128(wrow + (uint32_t)((ow * RPL + m) * GWW * sizeof(T)));
+                    vy[m] = lds128(wrow + (uint32_t)(((ow * RPL + m) * GWW + 16) * sizeof(T)));
+                }
 #pragma unroll
-                        for (int t = 0; t < RPL; ++t) {
-                            X[t] = fma_t(cX[t], ab, X[t]);
-                            Y[t] = fma_t(cY[t], ab, Y[t]);
-                        }
-                    }
+                for (int m = 0; m < RPL; ++m) {
+                    T cX[RPL], cY[RPL];                  // RPL * sizeof(T) == 16
+                    memcpy(cX, &vx[m], 16);
+                    memcpy(cY, &vy[m], 16);
+                    // e_step.hpp:613-623 with the operations off the critical path hoisted: hm = half_var_tau*mu_mult,
+                    // ndqeo = -dq*eta_old  =>  dq*eta_diff = fma(gamma, dq*mu, -dq*eta_old)
+                    const T r = add_t(bt[m], -X[m]);
+                    const T mu = mul_t(mm[m], r);                            // :613
+                    const T gam = sigmoid_t(fma_t(mul_t(hm[m], r), mu, ul[m]));   // :616-617
+                    const T al = fma_t(gam, mul_t(dq, mu), ndqeo[m]);        // :620, :623
+                    const T ab = shfl_t(al, src_lane);
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) X[t] = fma_t(cX[t], ab, X[t]);
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) Y[t] = fma_t(cY[t], ab, Y[t]);
+                    o_mu[m] = own ? mu : o_mu[m];
+                    o_g[m] = own ? gam : o_g[m];
+                    o_al[m] = own ? al : o_al[m];
+                }
+            }
+            // panel outputs: every lane owns RPL rows of its grid column
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const int cl = RPL * w + m;
+                const T av = (gvalid && j0 + cl < B) ? o_al[m] : T(0);
+                const uint32_t ad = a_alpha + (uint32_t)((((u % GAR) * GP + cl) * GT + g) * 8);
+                if constexpr (F32) {
+                    asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ad), "f"(av) : "memory");
+                } else {
+                    sts_t(ad, av);
+                }
+                if (gvalid && j0 + cl < B) {
+                    const size_t idx = colbase + (size_t)(j0 + cl);
+                    const T d = fma_t(o_g[m], o_mu[m], -eo[m]);               // :620
+                    a.var_mu[idx] = o_mu[m]; a.var_gamma[idx] = o_g[m]; a.eta_diff[idx] = d;
+                    a.eta[idx] = add_t(eo[m], d);                             // :633
                 }
             }
             __syncwarp();
