@@ -99,22 +99,22 @@ int viprs_b200_ld_destroy(viprs_b200_ld_t* ld);
  * from `eta`, which must therefore be consistent with (var_gamma, var_mu) as it is in the reference
  * (VIPRS.py:355-358).
  *
- * sums (optional, may be NULL): device double[VIPRS_B200_NSUMS] receiving the per-sweep reductions
- * the M-step / ELBO need (see VIPRS_B200_S_* below).
+ * The reductions the M-step / ELBO need are produced by viprs_b200_sums_* (VIPRS_B200_S_* slots below).
  */
-#define VIPRS_B200_NSUMS 12
-#define VIPRS_B200_S_GAMMA        0  /* sum gamma_j                         (VIPRS.py:434)          */
-#define VIPRS_B200_S_GAMMA_MU2    1  /* sum gamma_j mu_j^2                  (zeta, VIPRS.py:896)    */
-#define VIPRS_B200_S_ETA_QF       2  /* sum eta_j * qF_j ; eta'(R-I)eta = 2x (VIPRS.py:455)          */
-#define VIPRS_B200_S_BETA_ETA     3  /* sum std_beta_j eta_j                (VIPRS.py:469)          */
-#define VIPRS_B200_S_G_LOGG       4  /* sum g log g, g clipped [1e-15,1-1e-15] (VIPRS.py:512,562)   */
-#define VIPRS_B200_S_NG_LOGNG     5  /* sum (1-g) log(1-g), clipped         (VIPRS.py:516,563)      */
-#define VIPRS_B200_S_ETA2         6  /* sum eta_j^2                         (VIPRS.py:703)          */
-#define VIPRS_B200_S_MAX_DIFF     7  /* max |eta_diff_j|                    (VIPRS.py:997)          */
-#define VIPRS_B200_S_G_INV_TAU    8  /* sum gamma_j / var_tau_j   (needs n_per_snp; else 0)         */
-#define VIPRS_B200_S_G_LOG_TAU    9  /* sum gamma_j log var_tau_j (needs n_per_snp; else 0)         */
-#define VIPRS_B200_S_GCLIP        10 /* sum of clipped gamma_j              (VIPRS.py:565)          */
-#define VIPRS_B200_S_RESERVED     11
+#define VIPRS_B200_NSUMS 16
+#define VIPRS_B200_S_GAMMA        0  /* sum gamma                             (VIPRS.py:434, VIPRSMix.py:233)  */
+#define VIPRS_B200_S_GAMMA_MU2    1  /* sum gamma mu^2                        (zeta, VIPRS.py:896)             */
+#define VIPRS_B200_S_ETA_Q        2  /* q_scale * sum eta q                   (VIPRS.py:455)                   */
+#define VIPRS_B200_S_BETA_ETA     3  /* sum std_beta eta                      (VIPRS.py:469)                   */
+#define VIPRS_B200_S_G_LOGG       4  /* sum gc log gc, gc = clip(gamma, 1e-15, 1-1e-15)   (VIPRS.py:509,562)   */
+#define VIPRS_B200_S_NG_LOGNG     5  /* sum ngc log ngc, ngc = clip(1 - pip)  (VIPRS.py:514-518,563)           */
+#define VIPRS_B200_S_ETA2         6  /* sum eta^2                             (VIPRS.py:703)                   */
+#define VIPRS_B200_S_MAX_DIFF     7  /* max |eta_diff|                        (VIPRS.py:997)                   */
+#define VIPRS_B200_S_G_INV_TAU    8  /* sum gamma / var_tau                   (zeta, VIPRS.py:896)             */
+#define VIPRS_B200_S_G_LOG_TAU    9  /* sum gc log var_tau(theta_logtau)      (VIPRS.py:519,565)               */
+#define VIPRS_B200_S_GCLIP        10 /* sum gc                                (VIPRS.py:562,565)               */
+#define VIPRS_B200_S_GC_ZETA      11 /* sum gc (mu^2 + 1/var_tau)             (VIPRS.py:571-573, mixture)      */
+#define VIPRS_B200_S_NGCLIP       12 /* sum ngc                               (VIPRS.py:563)                   */
 
 int viprs_b200_e_step_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
                           float* var_mu, float* eta, float* q, float* eta_diff,
@@ -181,6 +181,44 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
                                   void* eta, void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
                                   const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
                                   int32_t threads, int32_t low_memory);
+
+/* ---- the per-iteration work around the sweep ------------------------------------------------------------
+ *
+ * theta: DEVICE double[ncol][4] = {sigma_epsilon, tau_beta, pi, lambda_min} per model column (grid) or per mixture
+ * component (sigma_epsilon and lambda_min repeated).  layout 0: (M, ncol) arrays are column-major (single model:
+ * ncol = 1; grid), layout 1: row-major (mixture, ncol = K).
+ *
+ * viprs_b200_prepare_*: the numpy pre-compute of VIPRS.e_step() / VIPRSMix.e_step() (VIPRS.py:400-406,418;
+ * VIPRSMix.py:187-204) in float64, cast to the state type: u_logs, mu_mult and tau_term = sqrt(var_tau/2)
+ * (half_tau = 0; cpp_e_step / cpp_e_step_mixture) or var_tau/2 (half_tau = 1; cpp_e_step_grid).  log_null_pi
+ * (M entries, mixture only) may be NULL. */
+int viprs_b200_prepare_f32(int32_t M, int32_t ncol, int32_t layout, int32_t half_tau, const double* n_per_snp,
+                           const double* theta, float* u_logs, float* tau_term, float* mu_mult, float* log_null_pi,
+                           void* stream);
+int viprs_b200_prepare_f64(int32_t M, int32_t ncol, int32_t layout, int32_t half_tau, const double* n_per_snp,
+                           const double* theta, double* u_logs, double* tau_term, double* mu_mult,
+                           double* log_null_pi, void* stream);
+
+/* viprs_b200_sums_*: sums[nseg][ncol][VIPRS_B200_NSUMS] (device doubles) over the row segments
+ * [seg_ptr[s], seg_ptr[s+1]) (chromosomes; device int32[nseg+1]) -- everything m_step() / elbo() / mse() and the
+ * convergence test read from the per-SNP arrays (VIPRS.py:426-484, 497-581, 689-704, 997; VIPRSMix.py:227-260).
+ * float64 accumulation in a fixed order (bit-reproducible).  eta / q / eta_diff / std_beta: M entries (layout 1)
+ * or (M, ncol) column-major (layout 0); mixture per-SNP slots (ETA_Q, BETA_ETA, NG_*, ETA2, MAX_DIFF) are
+ * reported in column 0.  q_scale multiplies sum eta*q: 2 when q holds only the forward part of the one-pass
+ * sweep (materialize_q = 0), else 1.  theta_logtau (may be NULL = theta) parameterises the cached log var_tau
+ * of the ELBO (VIPRS.py:401,519 -- VIPRSMix never refreshes it).  workspace: viprs_b200_sums_workspace_bytes()
+ * bytes of device memory, zero-filled once by the caller. */
+int64_t viprs_b200_sums_workspace_bytes(int32_t M, int32_t ncol, int32_t nseg);
+int viprs_b200_sums_f32(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, const int32_t* seg_ptr,
+                        const float* var_gamma, const float* var_mu, const float* eta, const float* q,
+                        const float* eta_diff, const float* std_beta, const double* n_per_snp, const double* theta,
+                        const double* theta_logtau, double q_scale, void* workspace, int64_t workspace_bytes,
+                        double* sums, void* stream);
+int viprs_b200_sums_f64(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, const int32_t* seg_ptr,
+                        const double* var_gamma, const double* var_mu, const double* eta, const double* q,
+                        const double* eta_diff, const double* std_beta, const double* n_per_snp, const double* theta,
+                        const double* theta_logtau, double q_scale, void* workspace, int64_t workspace_bytes,
+                        double* sums, void* stream);
 
 /* cpp_e_step_grid(...) (e_step_cpp.pyx:161-195) with host buffers; (M,G) arrays Fortran-order, active_model_idx
  * a host array of n_active column indices.  q is in/out. */

@@ -443,3 +443,53 @@ class OracleVIPRSMix(OracleVIPRS):
         var_tau = _dict_concat(self.var_tau)
         elbo -= .5 * (np.multiply(var_gamma, tau_beta) * (var_mu ** 2 + 1. / var_tau)).sum(axis=sum_axis)
         return elbo
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy restatement of the reduced sums (include/viprs_b200.h VIPRS_B200_S_*): what m_step()/elbo()/mse() read
+# from the per-SNP arrays (VIPRS.py:426-484, 497-581, 689-704; VIPRSMix.py:227-260), one row per model column /
+# mixture component.  Checker for viprs_b200_sums_* and for the host M-step in viprs_b200/em_host.py.
+# ---------------------------------------------------------------------------------------------
+NSUMS = 16
+
+
+def sums_numpy(var_gamma, var_mu, eta, q, eta_diff, std_beta, n_per_snp, theta, theta_logtau=None, q_scale=1.0,
+               mixture=False):
+    """var_gamma / var_mu: (M,), (M,G) [grid] or (M,K) [mixture=True]; theta: (ncol, 4) = sigma_eps, tau_beta, pi, lambda."""
+    res = np.finfo(np.float64).resolution
+    g = np.asarray(var_gamma, dtype=np.float64).reshape(len(std_beta), -1)
+    mu = np.asarray(var_mu, dtype=np.float64).reshape(len(std_beta), -1)
+    ncol = g.shape[1]
+    theta = np.asarray(theta, dtype=np.float64).reshape(ncol, 4)
+    tl = theta if theta_logtau is None else np.asarray(theta_logtau, dtype=np.float64).reshape(ncol, 4)
+    n = np.asarray(n_per_snp, dtype=np.float64)[:, None]
+    vt = n * (1. + theta[:, 3]) / theta[:, 0] + theta[:, 1]
+    lvt = np.log(n * (1. + tl[:, 3]) / tl[:, 0] + tl[:, 1])
+    gc = np.clip(g, res, 1. - res)
+    out = np.zeros((ncol, NSUMS))
+    out[:, 0] = g.sum(0)
+    out[:, 1] = (g * mu * mu).sum(0)
+    out[:, 8] = (g / vt).sum(0)
+    out[:, 4] = (gc * np.log(gc)).sum(0)
+    out[:, 10] = gc.sum(0)
+    out[:, 9] = (gc * lvt).sum(0)
+    out[:, 11] = (gc * (mu * mu + 1. / vt)).sum(0)
+    beta = np.asarray(std_beta, dtype=np.float64)
+    if mixture:
+        pip = np.asarray(var_gamma).sum(axis=1).astype(np.float64)[:, None]
+        et = np.asarray(eta, dtype=np.float64)[:, None]
+        qq = np.asarray(q, dtype=np.float64)[:, None]
+        dd = np.asarray(eta_diff, dtype=np.float64)[:, None]
+        cols = slice(0, 1)
+    else:
+        pip, et = g, np.asarray(eta, dtype=np.float64).reshape(g.shape)
+        qq, dd = np.asarray(q, dtype=np.float64).reshape(g.shape), np.asarray(eta_diff, dtype=np.float64).reshape(g.shape)
+        cols = slice(0, ncol)
+    ng = np.clip(1. - pip, res, 1. - res)
+    out[cols, 2] = q_scale * (et * qq).sum(0)
+    out[cols, 3] = (beta[:, None] * et).sum(0)
+    out[cols, 5] = (ng * np.log(ng)).sum(0)
+    out[cols, 12] = ng.sum(0)
+    out[cols, 6] = (et * et).sum(0)
+    out[cols, 7] = np.abs(dd).max(0) if len(beta) else 0.
+    return out

@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_model_gpu.py -m gpu -x -q 2>&1 | tail -40

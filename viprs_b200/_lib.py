@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libviprs_b200.so")
 
 I8, I16, F32, F64 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
-NSUMS = 12
+NSUMS = 16
 
 
 class ViprsB200Error(RuntimeError):
@@ -50,6 +50,11 @@ SIGNATURES = {
     "viprs_b200_backward_dot_f64": (ctypes.c_int, [_vp, _vp, _vp, _f64, _vp]),
     "viprs_b200_cpp_e_step": (ctypes.c_int, [_i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
     "viprs_b200_cpp_e_step_mixture": (ctypes.c_int, [_i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 10 + [_f64, _i32, _i32]),
+    "viprs_b200_prepare_f32": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 7),
+    "viprs_b200_prepare_f64": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 7),
+    "viprs_b200_sums_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "viprs_b200_sums_f32": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 10 + [_f64, _vp, _i64, _vp, _vp]),
+    "viprs_b200_sums_f64": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 10 + [_f64, _vp, _i64, _vp, _vp]),
     "viprs_b200_cpp_e_step_grid": (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
 }
 

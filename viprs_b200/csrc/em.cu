@@ -1,0 +1,231 @@
+// viprs_b200 -- the per-iteration work around the sweep, as two streaming kernels (HBM-bound, a few tens of bytes per
+// SNP x model):
+//   prepare : what VIPRS.e_step() / VIPRSMix.e_step() compute in numpy before calling cpp_e_step*
+//             (/root/reference/viprs/model/VIPRS.py:400-406,418 ; VIPRSMix.py:187-204): var_tau, mu_mult, u_logs,
+//             sqrt(var_tau/2) (or var_tau/2 for the grid kernel, e_step.hpp:616), log_null_pi -- float64 arithmetic,
+//             cast to the state type like the reference.
+//   sums    : the reductions m_step() / elbo() / mse() / the convergence test need (VIPRS.py:426-484, 497-581,
+//             689-704, 997 ; VIPRSMix.py:227-260) -- float64 accumulation, fixed summation order (deterministic),
+//             per chromosome segment and per model column / mixture component.
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int EM_THREADS = 256;
+
+struct Theta { double sigma_epsilon, tau_beta, pi, lambda_min; };
+
+// layout 0: (M, ncol) column-major (single model: ncol = 1; grid), 1: (M, ncol) row-major (mixture, ncol = K)
+template <typename T>
+__global__ void __launch_bounds__(EM_THREADS) prepare_kernel(int M, int ncol, int layout, int half_tau,
+                                                             const double* __restrict__ n_per_snp,
+                                                             const Theta* __restrict__ theta, T* __restrict__ u_logs,
+                                                             T* __restrict__ tau_term, T* __restrict__ mu_mult,
+                                                             T* __restrict__ log_null_pi) {
+    const int c = blockIdx.y;
+    const Theta th = theta[c];
+    const double cst = log(th.pi) - log(1.0 - th.pi) + 0.5 * log(th.tau_beta);      // VIPRS.py:405
+    const double nscale = (1.0 + th.lambda_min) / th.sigma_epsilon;                 // VIPRS.py:400
+    double lnp = 0.0;
+    if (log_null_pi != nullptr && c == 0) {                                         // VIPRSMix.py:191-194
+        double s = 0.0;
+        for (int k = 0; k < ncol; ++k) s += theta[k].pi;
+        lnp = log(1.0 - s);
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+        const double n = n_per_snp[j];
+        const double vt = n * nscale + th.tau_beta;
+        const size_t e = layout == 0 ? (size_t)c * M + j : (size_t)j * ncol + c;
+        mu_mult[e] = (T)(n / (vt * th.sigma_epsilon));                              // VIPRS.py:404
+        u_logs[e] = (T)(cst - 0.5 * log(vt));                                       // VIPRS.py:405-406
+        tau_term[e] = (T)(half_tau ? 0.5 * vt : sqrt(0.5 * vt));                    // e_step.hpp:616 / VIPRS.py:418
+        if (log_null_pi != nullptr && c == 0) log_null_pi[j] = (T)lnp;
+    }
+}
+
+constexpr int NS = VIPRS_B200_NSUMS;
+
+__device__ __forceinline__ double clip_res(double g) {                              // VIPRS.py:509-518
+    const double res = 1e-15;                                                       // np.finfo(np.float64).resolution
+    return fmin(fmax(g, res), 1.0 - res);
+}
+
+// grid = (chunks, nseg, ncol).  partial[((seg * ncol + c) * chunks + chunk) * NS + slot]; the last CTA of every
+// (seg, c) adds the chunk partials in chunk order and writes sums[(seg * ncol + c) * NS + slot].
+template <typename T>
+__global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int layout, const int32_t* __restrict__ seg_ptr,
+                                                          const T* __restrict__ var_gamma, const T* __restrict__ var_mu,
+                                                          const T* __restrict__ eta, const T* __restrict__ q,
+                                                          const T* __restrict__ eta_diff, const T* __restrict__ std_beta,
+                                                          const double* __restrict__ n_per_snp,
+                                                          const Theta* __restrict__ theta,
+                                                          const Theta* __restrict__ theta_logtau, double q_scale,
+                                                          double* __restrict__ partial, unsigned int* __restrict__ counters,
+                                                          double* __restrict__ sums) {
+    const int chunk = blockIdx.x, chunks = gridDim.x, seg = blockIdx.y, c = blockIdx.z;
+    const int row0 = seg_ptr[seg], row1 = seg_ptr[seg + 1];
+    const Theta th = theta[c], tl = theta_logtau[c];
+    const double nscale = (1.0 + th.lambda_min) / th.sigma_epsilon;
+    const double nscale_l = (1.0 + tl.lambda_min) / tl.sigma_epsilon;
+    const bool per_snp = (layout == 0) || (c == 0);       // mixture: eta / q / pip terms are per SNP, kept in column 0
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+    for (int j = row0 + chunk * blockDim.x + threadIdx.x; j < row1; j += chunks * blockDim.x) {
+        const size_t e = layout == 0 ? (size_t)c * M + j : (size_t)j * ncol + c;
+        const double g = (double)var_gamma[e];
+        const double mu = (double)var_mu[e];
+        const double n = n_per_snp[j];
+        const double vt = n * nscale + th.tau_beta;
+        const double gc = clip_res(g);
+        acc[VIPRS_B200_S_GAMMA] += g;                                               // VIPRS.py:434
+        acc[VIPRS_B200_S_GAMMA_MU2] += g * mu * mu;                                 // zeta, VIPRS.py:896
+        acc[VIPRS_B200_S_G_INV_TAU] += g / vt;
+        acc[VIPRS_B200_S_G_LOGG] += gc * log(gc);                                   // VIPRS.py:562
+        acc[VIPRS_B200_S_GCLIP] += gc;
+        acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(n * nscale_l + tl.tau_beta);        // VIPRS.py:565 (log_var_tau cache)
+        acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + 1.0 / vt);                     // VIPRS.py:571-573
+        if (per_snp) {
+            const size_t ev = layout == 0 ? e : (size_t)j;
+            const double et = (double)eta[ev];
+            double pip;
+            if (layout == 0) {
+                pip = g;
+            } else {                                                               // VIPRSMix.py:297-301 (sum in T)
+                T s = T(0);
+                for (int k = 0; k < ncol; ++k) s += var_gamma[(size_t)j * ncol + k];
+                pip = (double)s;
+            }
+            const double ng = clip_res(1.0 - pip);
+            acc[VIPRS_B200_S_ETA_Q] += q_scale * et * (double)q[ev];                // VIPRS.py:455
+            acc[VIPRS_B200_S_BETA_ETA] += (double)std_beta[j] * et;                 // VIPRS.py:469
+            acc[VIPRS_B200_S_NG_LOGNG] += ng * log(ng);                             // VIPRS.py:563
+            acc[VIPRS_B200_S_NGCLIP] += ng;
+            acc[VIPRS_B200_S_ETA2] += et * et;                                      // VIPRS.py:703
+            acc[VIPRS_B200_S_MAX_DIFF] = fmax(acc[VIPRS_B200_S_MAX_DIFF], fabs((double)eta_diff[ev]));   // VIPRS.py:997
+        }
+    }
+    // block reduction in a fixed order: lanes by xor-shuffle, then warps 0..7 sequentially
+    __shared__ double red[EM_THREADS / WARP][NS];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x % WARP, warp = threadIdx.x / WARP;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double v = acc[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(v, w) : v + w;
+        }
+        if (lane == 0) red[warp][s] = v;
+    }
+    __syncthreads();
+    const size_t slot = (size_t)seg * ncol + c;
+    if (threadIdx.x < NS) {
+        const int s = threadIdx.x;
+        double v = red[0][s];
+        for (int w = 1; w < EM_THREADS / WARP; ++w) v = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(v, red[w][s]) : v + red[w][s];
+        partial[(slot * chunks + chunk) * NS + s] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&counters[slot], 1u) == (unsigned int)(chunks - 1));
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < NS) {
+            const int s = threadIdx.x;
+            const volatile double* pp = partial + slot * chunks * NS;
+            double v = pp[s];
+            for (int k = 1; k < chunks; ++k) v = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(v, pp[k * NS + s]) : v + pp[k * NS + s];
+            sums[slot * NS + s] = v;
+        }
+        if (threadIdx.x == 0) counters[slot] = 0u;         // ready for the next call on this stream
+    }
+}
+
+static int sums_chunks(int M, int nseg) {
+    int per_seg = (M + nseg - 1) / (nseg > 0 ? nseg : 1);
+    int ch = (per_seg + 4 * EM_THREADS - 1) / (4 * EM_THREADS);
+    if (ch < 1) ch = 1;
+    if (ch > 32) ch = 32;
+    return ch;
+}
+
+template <typename T>
+static int prepare_dispatch(int M, int ncol, int layout, int half_tau, const double* n, const double* theta, T* u_logs,
+                            T* tau_term, T* mu_mult, T* log_null_pi, cudaStream_t st) {
+    if (M <= 0 || ncol <= 0 || !n || !theta || !u_logs || !tau_term || !mu_mult) return VIPRS_B200_EINVAL;
+    if (layout != 0 && layout != 1) return VIPRS_B200_EINVAL;
+    int bx = (M + EM_THREADS - 1) / EM_THREADS;
+    if (bx > 1184) bx = 1184;                       // 8 x 148: grid-stride beyond that
+    dim3 grid(bx, ncol);
+    prepare_kernel<T><<<grid, EM_THREADS, 0, st>>>(M, ncol, layout, half_tau, n, reinterpret_cast<const Theta*>(theta),
+                                                   u_logs, tau_term, mu_mult, log_null_pi);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+template <typename T>
+static int sums_dispatch(int M, int ncol, int layout, int nseg, const int32_t* seg_ptr, const T* var_gamma, const T* var_mu,
+                         const T* eta, const T* q, const T* eta_diff, const T* std_beta, const double* n,
+                         const double* theta, const double* theta_logtau, double q_scale, void* workspace,
+                         int64_t workspace_bytes, double* sums, cudaStream_t st) {
+    if (M <= 0 || ncol <= 0 || nseg <= 0 || !seg_ptr || !var_gamma || !var_mu || !eta || !q || !eta_diff || !std_beta ||
+        !n || !theta || !workspace || !sums)
+        return VIPRS_B200_EINVAL;
+    if (layout != 0 && layout != 1) return VIPRS_B200_EINVAL;
+    if (ncol > 65535 || nseg > 65535) return VIPRS_B200_EINVAL;
+    const int chunks = sums_chunks(M, nseg);
+    const int64_t need_c = (((int64_t)nseg * ncol * 4 + 255) / 256) * 256;
+    const int64_t need = need_c + (int64_t)nseg * ncol * chunks * NS * 8;
+    if (workspace_bytes < need) return VIPRS_B200_EINVAL;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);      // zeroed by the caller once; self-resetting
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + need_c);
+    dim3 grid(chunks, nseg, ncol);
+    sums_kernel<T><<<grid, EM_THREADS, 0, st>>>(M, ncol, layout, seg_ptr, var_gamma, var_mu, eta, q, eta_diff, std_beta, n,
+                                                reinterpret_cast<const Theta*>(theta),
+                                                reinterpret_cast<const Theta*>(theta_logtau ? theta_logtau : theta), q_scale,
+                                                partial, counters, sums);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+}  // namespace vb
+
+extern "C" int64_t viprs_b200_sums_workspace_bytes(int32_t M, int32_t ncol, int32_t nseg) {
+    if (M <= 0 || ncol <= 0 || nseg <= 0) return 0;
+    const int chunks = vb::sums_chunks(M, nseg);
+    return (((int64_t)nseg * ncol * 4 + 255) / 256) * 256 + (int64_t)nseg * ncol * chunks * vb::NS * 8;
+}
+
+extern "C" int viprs_b200_prepare_f32(int32_t M, int32_t ncol, int32_t layout, int32_t half_tau, const double* n_per_snp,
+                                      const double* theta, float* u_logs, float* tau_term, float* mu_mult,
+                                      float* log_null_pi, void* stream) {
+    return vb::prepare_dispatch<float>(M, ncol, layout, half_tau, n_per_snp, theta, u_logs, tau_term, mu_mult, log_null_pi,
+                                       (cudaStream_t)stream);
+}
+extern "C" int viprs_b200_prepare_f64(int32_t M, int32_t ncol, int32_t layout, int32_t half_tau, const double* n_per_snp,
+                                      const double* theta, double* u_logs, double* tau_term, double* mu_mult,
+                                      double* log_null_pi, void* stream) {
+    return vb::prepare_dispatch<double>(M, ncol, layout, half_tau, n_per_snp, theta, u_logs, tau_term, mu_mult, log_null_pi,
+                                        (cudaStream_t)stream);
+}
+extern "C" int viprs_b200_sums_f32(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, const int32_t* seg_ptr,
+                                   const float* var_gamma, const float* var_mu, const float* eta, const float* q,
+                                   const float* eta_diff, const float* std_beta, const double* n_per_snp,
+                                   const double* theta, const double* theta_logtau, double q_scale, void* workspace,
+                                   int64_t workspace_bytes, double* sums, void* stream) {
+    return vb::sums_dispatch<float>(M, ncol, layout, nseg, seg_ptr, var_gamma, var_mu, eta, q, eta_diff, std_beta, n_per_snp,
+                                    theta, theta_logtau, q_scale, workspace, workspace_bytes, sums, (cudaStream_t)stream);
+}
+extern "C" int viprs_b200_sums_f64(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, const int32_t* seg_ptr,
+                                   const double* var_gamma, const double* var_mu, const double* eta, const double* q,
+                                   const double* eta_diff, const double* std_beta, const double* n_per_snp,
+                                   const double* theta, const double* theta_logtau, double q_scale, void* workspace,
+                                   int64_t workspace_bytes, double* sums, void* stream) {
+    return vb::sums_dispatch<double>(M, ncol, layout, nseg, seg_ptr, var_gamma, var_mu, eta, q, eta_diff, std_beta, n_per_snp,
+                                     theta, theta_logtau, q_scale, workspace, workspace_bytes, sums, (cudaStream_t)stream);
+}
