@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
     const double nscale = (1.0 + th.lambda_min) / th.sigma_epsilon;
     const double nscale_l = (1.0 + tl.lambda_min) / tl.sigma_epsilon;
     const bool per_snp = (layout == 0) || (c == 0);       // mixture: eta / q / pip terms are per SNP, kept in column 0
+    const bool same_tau = (theta_logtau == theta);
     double acc[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[s] = 0.0;
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
         const double gc = clip_res(g);
         acc[VIPRS_B200_S_GAMMA] += g;                                               // VIPRS.py:434
         acc[VIPRS_B200_S_GAMMA_MU2] += g * mu * mu;                                 // zeta, VIPRS.py:896
-        acc[VIPRS_B200_S_G_INV_TAU] += g / vt;
+        const double ivt = 1.0 / vt;
+        acc[VIPRS_B200_S_G_INV_TAU] += g * ivt;
         acc[VIPRS_B200_S_G_LOGG] += gc * log(gc);                                   // VIPRS.py:562
         acc[VIPRS_B200_S_GCLIP] += gc;
-        acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(n * nscale_l + tl.tau_beta);        // VIPRS.py:565 (log_var_tau cache)
-        acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + 1.0 / vt);                     // VIPRS.py:571-573
+        acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(same_tau ? vt : n * nscale_l + tl.tau_beta);   // VIPRS.py:565 (log_var_tau cache)
+        acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);                          // VIPRS.py:571-573
         if (per_snp) {
             const size_t ev = layout == 0 ? e : (size_t)j;
             const double et = (double)eta[ev];
@@ -135,22 +137,37 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
     __syncthreads();
     if (is_last) {
         __threadfence();
+        // fixed-order, 16-way parallel: thread (k0, s) folds chunks k0, k0+16, ... of slot s, then slot s folds its 16 partials
+        constexpr int KW = EM_THREADS / NS;
+        const int s = threadIdx.x % NS, k0 = threadIdx.x / NS;
+        const double* pp = partial + slot * chunks * NS;
+        double v = 0.0;
+        for (int k = k0; k < chunks; k += KW) {
+            const double w = __ldcg(pp + k * NS + s);
+            v = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(v, w) : v + w;
+        }
+        __shared__ double red2[KW][NS];
+        red2[k0][s] = v;
+        __syncthreads();
         if (threadIdx.x < NS) {
-            const int s = threadIdx.x;
-            const volatile double* pp = partial + slot * chunks * NS;
-            double v = pp[s];
-            for (int k = 1; k < chunks; ++k) v = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(v, pp[k * NS + s]) : v + pp[k * NS + s];
-            sums[slot * NS + s] = v;
+            double t = red2[0][s];
+            for (int k = 1; k < KW; ++k) t = (s == VIPRS_B200_S_MAX_DIFF) ? fmax(t, red2[k][s]) : t + red2[k][s];
+            sums[slot * NS + s] = t;
         }
         if (threadIdx.x == 0) counters[slot] = 0u;         // ready for the next call on this stream
     }
 }
 
-static int sums_chunks(int M, int nseg) {
-    int per_seg = (M + nseg - 1) / (nseg > 0 ? nseg : 1);
-    int ch = (per_seg + 4 * EM_THREADS - 1) / (4 * EM_THREADS);
+// CTAs per (segment, column): ~2 rows per thread (the float64 logarithms dominate, so parallelism matters more than
+// bytes), capped so that the whole grid stays within 64K CTAs and the partial buffer within a few tens of MB.
+static int sums_chunks(int M, int ncol, int nseg) {
+    const int per_seg = (M + nseg - 1) / (nseg > 0 ? nseg : 1);
+    int ch = (per_seg + 2 * EM_THREADS - 1) / (2 * EM_THREADS);
+    const int64_t slots = (int64_t)nseg * ncol;
+    const int cap = (int)(65536 / (slots > 0 ? slots : 1));
+    if (ch > cap) ch = cap;
+    if (ch > 1024) ch = 1024;
     if (ch < 1) ch = 1;
-    if (ch > 32) ch = 32;
     return ch;
 }
 
@@ -178,7 +195,7 @@ static int sums_dispatch(int M, int ncol, int layout, int nseg, const int32_t* s
         return VIPRS_B200_EINVAL;
     if (layout != 0 && layout != 1) return VIPRS_B200_EINVAL;
     if (ncol > 65535 || nseg > 65535) return VIPRS_B200_EINVAL;
-    const int chunks = sums_chunks(M, nseg);
+    const int chunks = sums_chunks(M, ncol, nseg);
     const int64_t need_c = (((int64_t)nseg * ncol * 4 + 255) / 256) * 256;
     const int64_t need = need_c + (int64_t)nseg * ncol * chunks * NS * 8;
     if (workspace_bytes < need) return VIPRS_B200_EINVAL;
@@ -197,7 +214,7 @@ static int sums_dispatch(int M, int ncol, int layout, int nseg, const int32_t* s
 
 extern "C" int64_t viprs_b200_sums_workspace_bytes(int32_t M, int32_t ncol, int32_t nseg) {
     if (M <= 0 || ncol <= 0 || nseg <= 0) return 0;
-    const int chunks = vb::sums_chunks(M, nseg);
+    const int chunks = vb::sums_chunks(M, ncol, nseg);
     return (((int64_t)nseg * ncol * 4 + 255) / 256) * 256 + (int64_t)nseg * ncol * chunks * vb::NS * 8;
 }
 

@@ -54,7 +54,7 @@ class VIPRS:
 
     def __init__(self, gdl=None, fix_params=None, tracked_params=None, lambda_min=None, float_precision="float32",
                  order="F", low_memory=True, dequantize_on_the_fly=False, threads=1, data=None, device=None,
-                 shard=False, group=None):
+                 shard=False, presharded=False, group=None):
         assert float_precision in _TORCH_FLOAT
         if not torch.cuda.is_available():
             raise _lib.ViprsB200Error(-5, "VIPRS (viprs_b200 has no CPU fallback)")
@@ -88,13 +88,23 @@ class VIPRS:
 
         # ---- sharding: whole LD blocks per rank ----
         self.rank, self.world, self.group = 0, 1, group
-        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+        if (shard or presharded) and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank = torch.distributed.get_rank(group)
             self.world = torch.distributed.get_world_size(group)
         # global shapes (BayesPRSModel.py:60-75)
         self.shapes = {c: int(len(data[c]["std_beta"])) for c in self.chromosomes}
         self._n = float(max(float(torch.as_tensor(data[c]["n_per_snp"]).max()) for c in self.chromosomes))
-        if self.world > 1:
+        if self.world > 1 and presharded:
+            # `data` is already this rank's shard (whole LD blocks): only the global sizes are exchanged
+            import torch.distributed as dist
+            sz = torch.tensor([float(self.shapes[c]) for c in self.chromosomes] + [0.0], dtype=torch.float64, device=self.device)
+            dist.all_reduce(sz, op=dist.ReduceOp.SUM, group=group)
+            mx = torch.tensor([self._n], dtype=torch.float64, device=self.device)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+            self.row_ranges = {c: (0, self.shapes[c]) for c in self.chromosomes}
+            self.shapes = {c: int(v) for c, v in zip(self.chromosomes, sz.tolist())}
+            self._n = float(mx.item())
+        elif self.world > 1:
             plan = shard_genome({c: {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in data[c].items()
                                      if k in ("ld_left_bound", "ld_indptr")} for c in self.chromosomes}, self.world)
             self.row_ranges = plan[self.rank]
@@ -357,11 +367,11 @@ class VIPRS:
             if self.M > 0:
                 L = _lib.lib()
                 fn = L.viprs_b200_sums_f32 if self._tdt == torch.float32 else L.viprs_b200_sums_f64
-                tl = torch.from_numpy(self._theta_logtau_for_sums()).to(self.device)
+                tl = self._theta_logtau_dev()
                 rc = fn(self.M, self._ncol, self._layout, len(self.chromosomes), self._seg_dev.data_ptr(),
                         self._g.data_ptr(), self._mu.data_ptr(), self._eta.data_ptr(), self._q.data_ptr(),
                         self._diff.data_ptr(), self.std_beta_dev.data_ptr(), self.n_per_snp_dev.data_ptr(),
-                        self._theta_dev.data_ptr(), tl.data_ptr(), 2.0 if self._q_is_forward else 1.0,
+                        self._theta_dev.data_ptr(), tl, 2.0 if self._q_is_forward else 1.0,
                         self._ws.data_ptr(), self._ws.numel(), self._sums_dev.data_ptr(), _stream_ptr())
                 _lib.check(rc, "viprs_b200_sums")
             else:
@@ -369,8 +379,9 @@ class VIPRS:
             self._sums = self._exchange.all_reduce(self._sums_dev)
         return self._sums
 
-    def _theta_logtau_for_sums(self):
-        return self._theta_last            # VIPRS.e_step refreshes the log(var_tau) cache every iteration (VIPRS.py:401)
+    def _theta_logtau_dev(self):
+        # VIPRS.e_step refreshes the log(var_tau) cache every iteration (VIPRS.py:401): same theta as the sweep (NULL)
+        return None
 
     def _seg_sizes(self):
         return np.array([self.shapes[c] for c in self.chromosomes], dtype=np.float64)
@@ -596,10 +607,13 @@ class VIPRSMix(VIPRS):
                               self._ul, self._tt, self._mm, self.dequantize_scale, False)
         self._q_is_forward = True
 
-    def _theta_logtau_for_sums(self):
+    def _theta_logtau_dev(self):
         # VIPRSMix.e_step never refreshes `_log_var_tau` (VIPRSMix.py:187-204 takes np.log(var_tau) inline), so the
         # reference's elbo() (VIPRS.py:519) keeps reading the value cached at initialisation (VIPRS.py:359).
-        return self._theta_logtau
+        if getattr(self, "_tl_dev_src", None) is not self._theta_logtau:
+            self._tl_dev = torch.from_numpy(self._theta_logtau).to(self.device)
+            self._tl_dev_src = self._theta_logtau
+        return self._tl_dev.data_ptr()
 
     def m_step(self):
         em_host.mix_m_step(self._reduce(), self.n_snps, self._hyp, self.fix_params)
