@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libviprs_b200.so")
+# VIPRS_B200_LIB: load an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("VIPRS_B200_LIB") or os.path.join(_HERE, "_C", "libviprs_b200.so")
 
 I8, I16, F32, F64 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_C")
+OUT_DIR = os.path.join(HERE, os.environ.get("VIPRS_B200_OUT", "_C"))     # VIPRS_B200_OUT: variant builds for A/B timing
 LIB = os.path.join(OUT_DIR, "libviprs_b200.so")
 SOURCES = ["ld.cu", "api.cu", "slab_f32.cu", "slab_f64.cu", "mix_f32.cu", "mix_f64.cu", "grid_f32.cu", "grid_f64.cu", "em.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -13,7 +13,8 @@
 // Warp roles (no __syncthreads after the prologue):
 //   warps 0..nbw-1  bulk : thread t owns GKPT = 16 columns x GT grid columns of q in REGISTERS for the whole
 //                      sweep (128 registers).  Per LD row: one 128-bit shared load of its 16 codes (int8), the GT
-//                      scaled deltas from a shared ring (broadcast loads), decode, 64 FFMA2 (or 64 DFMA).
+//                      scaled deltas from a shared ring (two broadcast loads), decode, 64 FFMA2 (or 64 DFMA); the
+//                      float tile pairs adjacent GRID columns so the decoded LD value is a 32-bit broadcast operand.
 //                      After every panel the owner of the columns two panels ahead publishes them for the chain.
 //   aux warp 0      producer : 1-D TMA bulk copies of (16 rows x <= 4 KB) stages into an nst-deep ring.
 //   aux warp 1      chain : lane = (grid column g, slot w).  Per 16-row panel it holds X[c,g] = published q + the
@@ -58,7 +59,7 @@ inline GridLayout make_grid_layout(int tsize, int gt, int stage_bytes, int nst) 
     L.wwin = o;   o += 2u * GP * GWW * (uint32_t)tsize;
     L.wraw = o;   o += (uint32_t)GP * GWW * 8u;                       // raw window, sized for 8-byte LD elements
     L.pbuf = o;   o += 2u * 5u * GP * (uint32_t)gt * (uint32_t)tsize;
-    L.alpha = o;  o += (uint32_t)GAR * GP * (uint32_t)gt * 8u;
+    L.alpha = o;  o += (uint32_t)GAR * GP * (uint32_t)gt * (uint32_t)tsize;
     L.qpub = o;   o += 2u * GP * (uint32_t)gt * (uint32_t)tsize;
     L.bars = o;   o += (2u * GNST_MAX + GAR) * 8u;
     L.prog = o;   o += GRID_MAX_BW * 4u;
@@ -332,12 +333,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
             for (int m = 0; m < RPL; ++m) {
                 const int cl = RPL * w + m;
                 const T av = (gvalid && j0 + cl < B) ? o_al[m] : T(0);
-                const uint32_t ad = a_alpha + (uint32_t)((((u % GAR) * GP + cl) * GT + g) * 8);
-                if constexpr (F32) {
-                    asm volatile("st.shared.v2.f32 [%0], {%1,%1};" ::"r"(ad), "f"(av) : "memory");
-                } else {
-                    sts_t(ad, av);
-                }
+                sts_t(a_alpha + (uint32_t)((((u % GAR) * GP + cl) * GT + g) * sizeof(T)), av);
                 if (gvalid && j0 + cl < B) {
                     const size_t idx = colbase + (size_t)(j0 + cl);
                     const T d = fma_t(o_g[m], o_mu[m], -eo[m]);               // :620
@@ -368,25 +364,28 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
             gval[g] = gi < p.n_active;
             gcol[g] = p.active[gval[g] ? gi : tile * GT];
         }
-        // q registers: float -> pairs of adjacent columns (FFMA2 along the column pair), double -> scalars
+        // q registers.  float: pairs of adjacent GRID columns, q2[col][gp] = (q[col][2gp], q[col][2gp+1]), so that one
+        // FFMA2 takes the decoded LD value as a 32-bit broadcast operand (R.F32), the two scaled deltas as a natural
+        // 64-bit pair from the ring, and the accumulator pair -- measured 13% faster than pairing along the LD columns
+        // (scratch/fma_bench4.cu).  double: scalars.
         using QT = typename std::conditional<F32, float2, double>::type;
-        constexpr int QE = F32 ? EPV / 2 : EPV;
-        QT qr[NVT][QE][GT];
+        constexpr int QG = F32 ? GT / 2 : GT;
+        QT qr[NVT][EPV][QG];
+        auto q_load = [&](int col, int g) -> T {
+            return (col < B && gval[g]) ? a.q[(size_t)gcol[g] * M + (size_t)r0 + col] : T(0);
+        };
 #pragma unroll
         for (int i = 0; i < NVT; ++i) {
             const int col0 = (t + NT * i) * EPV;
 #pragma unroll
-            for (int e = 0; e < QE; ++e) {
+            for (int e = 0; e < EPV; ++e) {
 #pragma unroll
-                for (int g = 0; g < GT; ++g) {
-                    const size_t cb = (size_t)gcol[g] * M + (size_t)r0;
+                for (int g = 0; g < QG; ++g) {
                     if constexpr (F32) {
-                        const int c0 = col0 + 2 * e;
-                        qr[i][e][g].x = (c0 < B && gval[g]) ? a.q[cb + c0] : 0.f;
-                        qr[i][e][g].y = (c0 + 1 < B && gval[g]) ? a.q[cb + c0 + 1] : 0.f;
+                        qr[i][e][g].x = q_load(col0 + e, 2 * g);
+                        qr[i][e][g].y = q_load(col0 + e, 2 * g + 1);
                     } else {
-                        const int c0 = col0 + e;
-                        qr[i][e][g] = (c0 < B && gval[g]) ? a.q[cb + c0] : 0.0;
+                        qr[i][e][g] = q_load(col0 + e, g);
                     }
                 }
             }
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         for (int u = 0; u < NP; ++u) {
             const int nrows = min(GP, B - u * GP);
             mbar_wait(&cdone[u % GAR], (u / GAR) & 1);
-            const uint32_t abase = a_alpha + (uint32_t)((u % GAR) * GP * GT * 8);
+            const uint32_t abase = a_alpha + (uint32_t)((u % GAR) * GP * GT * sizeof(T));
             for (int c = 0; c < nck; ++c) {
                 const int cb = min(GCW, row_bytes - c * GCW);
                 mbar_wait(&full[s], k & 1);
@@ -414,24 +413,24 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
 #pragma unroll
                 for (int i = 0; i < NVT; ++i) any |= (vchunk[i] == c);
                 if (any) {
-#pragma unroll 2
+                    // (a hand-pipelined variant that fetched row r+1's codes and deltas before row r's FMAs measured 1.5%
+                    // slower on B200: the second bulk warp of the sub-partition already covers the shared-memory latency)
+#pragma unroll 1
                     for (int r = 0; r < nrows; ++r) {
-                        // the GT scaled deltas of row r (float: stored duplicated, one float2 per grid column)
-                        QT al[GT];
+                        // the GT scaled deltas of row r: GT * sizeof(T) = 32 bytes, two broadcast loads
+                        const uint4 v0 = lds128(abase + (uint32_t)(r * GT * sizeof(T)));
+                        const uint4 v1 = lds128(abase + (uint32_t)(r * GT * sizeof(T) + 16));
+                        QT al[QG];
                         if constexpr (F32) {
-#pragma unroll
-                            for (int gg = 0; gg < GT; gg += 2) {
-                                const uint4 v = lds128(abase + (uint32_t)((r * GT + gg) * 8));
-                                al[gg] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
-                                al[gg + 1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
-                            }
+                            al[0] = make_float2(__uint_as_float(v0.x), __uint_as_float(v0.y));
+                            al[1] = make_float2(__uint_as_float(v0.z), __uint_as_float(v0.w));
+                            al[2] = make_float2(__uint_as_float(v1.x), __uint_as_float(v1.y));
+                            al[3] = make_float2(__uint_as_float(v1.z), __uint_as_float(v1.w));
                         } else {
-#pragma unroll
-                            for (int gg = 0; gg < GT; gg += 2) {
-                                const uint4 v = lds128(abase + (uint32_t)((r * GT + gg) * 8));
-                                al[gg] = __hiloint2double((int)v.y, (int)v.x);
-                                al[gg + 1] = __hiloint2double((int)v.w, (int)v.z);
-                            }
+                            al[0] = __hiloint2double((int)v0.y, (int)v0.x);
+                            al[1] = __hiloint2double((int)v0.w, (int)v0.z);
+                            al[2] = __hiloint2double((int)v1.y, (int)v1.x);
+                            al[3] = __hiloint2double((int)v1.w, (int)v1.z);
                         }
 #pragma unroll
                         for (int i = 0; i < NVT; ++i) {
@@ -440,11 +439,11 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                                 T v[EPV];
                                 GridDecode<T, U>::vec(cv, v);
 #pragma unroll
-                                for (int e = 0; e < QE; ++e) {
+                                for (int e = 0; e < EPV; ++e) {
 #pragma unroll
-                                    for (int g = 0; g < GT; ++g) {
+                                    for (int g = 0; g < QG; ++g) {
                                         if constexpr (F32) {
-                                            qr[i][e][g] = fma2(make_float2(v[2 * e], v[2 * e + 1]), al[g], qr[i][e][g]);
+                                            qr[i][e][g] = fma2(make_float2(v[e], v[e]), al[g], qr[i][e][g]);
                                         } else {
                                             qr[i][e][g] = fma(v[e], al[g], qr[i][e][g]);
                                         }
@@ -467,14 +466,15 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                     if (vv / NVT == pp) {
                         const int kk = (vv % NVT) * EPV;
 #pragma unroll
-                        for (int e = 0; e < QE; ++e) {
+                        for (int e = 0; e < EPV; ++e) {
 #pragma unroll
-                            for (int g = 0; g < GT; ++g) {
+                            for (int g = 0; g < QG; ++g) {
+                                const uint32_t ad = a_qpub + (uint32_t)((((pp & 1) * GP + kk + e) * GT) * sizeof(T));
                                 if constexpr (F32) {
-                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + 2 * e) * GT + g) * 4), qr[i][e][g].x);
-                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + 2 * e + 1) * GT + g) * 4), qr[i][e][g].y);
+                                    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(ad + (uint32_t)(8 * g)), "f"(qr[i][e][g].x),
+                                                 "f"(qr[i][e][g].y) : "memory");
                                 } else {
-                                    sts_t(a_qpub + (uint32_t)((((pp & 1) * GP + kk + e) * GT + g) * 8), qr[i][e][g]);
+                                    sts_t(ad + (uint32_t)(8 * g), qr[i][e][g]);
                                 }
                             }
                         }
@@ -489,18 +489,16 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         for (int i = 0; i < NVT; ++i) {
             const int col0 = (t + NT * i) * EPV;
 #pragma unroll
-            for (int e = 0; e < QE; ++e) {
+            for (int e = 0; e < EPV; ++e) {
+                const int col = col0 + e;
+                if (col >= B) continue;
 #pragma unroll
-                for (int g = 0; g < GT; ++g) {
-                    if (!gval[g]) continue;
-                    const size_t cb = (size_t)gcol[g] * M + (size_t)r0;
+                for (int g = 0; g < QG; ++g) {
                     if constexpr (F32) {
-                        const int c0 = col0 + 2 * e;
-                        if (c0 < B) a.q[cb + c0] = qr[i][e][g].x;
-                        if (c0 + 1 < B) a.q[cb + c0 + 1] = qr[i][e][g].y;
+                        if (gval[2 * g]) a.q[(size_t)gcol[2 * g] * M + (size_t)r0 + col] = qr[i][e][g].x;
+                        if (gval[2 * g + 1]) a.q[(size_t)gcol[2 * g + 1] * M + (size_t)r0 + col] = qr[i][e][g].y;
                     } else {
-                        const int c0 = col0 + e;
-                        if (c0 < B) a.q[cb + c0] = qr[i][e][g];
+                        if (gval[g]) a.q[(size_t)gcol[g] * M + (size_t)r0 + col] = qr[i][e][g];
                     }
                 }
             }

@@ -194,6 +194,13 @@ struct MixModel {
     }
 };
 
+// trips of the chain's 4-step group loop that are unrolled: a rolled loop keeps the chain warp's code inside the
+// instruction cache (the three warp roles execute disjoint code)
+#ifndef VB_CHAIN_UNROLL
+#define VB_CHAIN_UNROLL 1
+#endif
+constexpr int kChainUnroll = VB_CHAIN_UNROLL;
+
 template <typename T> __device__ __forceinline__ T eps_of();
 template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920928955078125e-7f; }   // max(FLT_EPSILON, 1e-8)
 template <> __device__ __forceinline__ double eps_of<double>() { return 1e-8; }                    // max(DBL_EPSILON, 1e-8)
@@ -337,7 +344,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             X0 += lds_t(a_f + (uint32_t)(cl & sm.fmask) * sizeof(T), T()) + bsum;
         }
         T Xown = T(0);
-#pragma unroll
+#pragma unroll kChainUnroll
         for (int h = 0; h < PMAX; h += 4) {
             if (h < nrows) {
                 T w0[4], w1[4];
