@@ -165,6 +165,9 @@ static int choose_stage_bytes(int max_block, int max_row_bytes, int smem_optin, 
     } else {
         const int st = max_block <= FAST_MAX_BLOCK ? (int)make_fast_layout(0, 0).total : state_bytes(max_block, 4);
         sb = (kSmemTwoPerSM - st) / 4;
+        // long rows: 8-row panels in a 3-deep ring beat 4-row panels in a 4-deep one (per-panel hand-off costs
+        // dominate the first quarter of a 4096-SNP block; measured 1.102 -> 1.069 ms on the C2 workload)
+        if (max_block <= FAST_MAX_BLOCK && (int64_t)max_row_bytes * 8 > sb) sb = ((kSmemTwoPerSM - st) / 3) & ~127;
         if (sb < max_row_bytes || sb < 2048) sb = (smem_optin - st) / 4;
         if (sb > 48 * 1024) sb = 48 * 1024;
     }

@@ -39,7 +39,7 @@ __device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && war
 constexpr int GT = 128;                   // threads per bulk group
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
-constexpr int HP = 264;                   // entries of the fixed-point prefix sum (>= 4096/16 + 1)
+constexpr int HP = 258;                   // entries of the fixed-point prefix sum (>= 4096/16 + 1; HP * 8 a multiple of 16)
 constexpr int NLIMB_MAX = 4;
 
 struct FastLayout {
@@ -57,7 +57,7 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     L.fring = o;     o += FR * 4;
     L.hc = o;        o += HP * 8;
     L.zero = o;      o += 32;
-    L.red = o;       o += 64;
+    L.red = L.partial;                   // prologue scratch, dead before the first partial is written
     L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
     L.counters = o;  o += (NAW + NCW) * (uint32_t)sizeof(uint32_t);
     L.total = o;
