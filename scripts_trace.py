@@ -37,4 +37,25 @@ for name, (x, y) in {"producer empty-wait": (PW0, PW1), "producer wait->issue": 
                      "chain done->C start(max)": (CD, C0max), "C: start->done (slowest)": (C0min, C1max),
                      "C done->next TMA issue": (C1max, {k - 4: v for k, v in P.items()})}.items():
     print(f"{name:26s}" + "".join(f"{avg(x, y, q[i], q[i + 1]):10.0f}" for i in range(4)))
+A3min, A3max, A6min, A6max = agg(AW, 3, min), agg(AW, 3, max), agg(AW, 6, min), agg(AW, 6, max)
+C6max = agg(CW, 6, max)
+if A3max:
+    for name, (x, y) in {"A: got->window done (max)": (AF1max, A3max), "A: window->groups done": (A3max, A6max), "A: epilogue": (A6max, ADmax),
+                         "A fastest warp got->done": (AF1min, ADmin), "C: groups (slowest)": (C0min, C6max), "C: publish": (C6max, C1max),
+                         "C fastest warp": (C0min, C1min)}.items():
+        print(f"{name:26s}" + "".join(f"{avg(x, y, q[i], q[i + 1]):10.0f}" for i in range(4)))
+def perwarp(w, e0, e1, lo, hi):
+    x, y = series(w, e0), series(w, e1)
+    return avg(x, y, lo, hi)
+print("per-warp phase durations (first half | second half of the block)")
+for w in AW:
+    print(f"  A{w}: wait-full " + " | ".join(f"{perwarp(w, 0, 1, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  window " + " | ".join(f"{perwarp(w, 1, 3, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  groups " + " | ".join(f"{perwarp(w, 3, 6, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  g0 math " + " | ".join(f"{perwarp(w, 3, 4, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  g0 redux " + " | ".join(f"{perwarp(w, 4, 5, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  epilogue " + " | ".join(f"{perwarp(w, 6, 2, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))
+for w in CW:
+    print(f"  C{w}: groups " + " | ".join(f"{perwarp(w, 4, 6, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
+          "  publish " + " | ".join(f"{perwarp(w, 6, 5, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))
 print("chain period/panel        " + "".join(f"{(CD[q[i + 1] - 1] - CD[q[i]]) / (q[i + 1] - 1 - q[i]):10.0f}" for i in range(4)))

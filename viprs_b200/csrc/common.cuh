@@ -364,6 +364,15 @@ __device__ __forceinline__ T sigmoid_t(T x) {
     return mul_t(num, fast_rcp_t(add_t(T(1), e)));
 }
 
+// the same sigmoid for a logit given in base-2 units (x * log2 e): e = 2^-|x2| straight from MUFU.EX2
+__device__ __forceinline__ float sigmoid2_t(float x2) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(x2)));
+    const float num = x2 < 0.f ? e : 1.f;
+    return __fmul_rn(num, fast_rcp_t(__fadd_rn(1.f, e)));
+}
+__device__ __forceinline__ double sigmoid2_t(double x2) { return sigmoid_t(x2 * 0.6931471805599453); }
+
 template <typename T>
 __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <typename T>

@@ -114,12 +114,21 @@ struct SlabModel {
         L.a0 = mul_t(r.sv, L.c0);            // u = sqrt_half_var_tau * mu  (:404), one FMA off X instead of two ops
         L.a1 = mul_t(r.sv, L.c1);
         L.ul = r.ul;
+        if constexpr (sizeof(T) == 4) {
+            // float: the logit is carried in base-2 units (u^2 + u_logs) * log2(e), so that the sigmoid's exponential
+            // is a bare MUFU.EX2 on the serial path (one multiply fewer per SNP)
+            L.a0 = mul_t(L.a0, T(1.2011224087864498));       // sqrt(log2 e)
+            L.a1 = mul_t(L.a1, T(1.2011224087864498));
+            L.ul = mul_t(L.ul, T(1.4426950408889634));
+        }
     }
     // X: F_j + B_j in LD-code units; eo: eta_j before the update
     static __device__ __forceinline__ void step(const Lane& L, T X, T eo, T eps, T& en, T& d, bool& skip, Out& o) {
         const T mu = fma_t(L.c1, X, L.c0);
         const T uu = fma_t(L.a1, X, L.a0);                        // :404
-        const T g = sigmoid_t(fma_t(uu, uu, L.ul));               // :405
+        T g;
+        if constexpr (sizeof(T) == 4) g = sigmoid2_t(fma_t(uu, uu, L.ul));     // :405, logit in base-2 units
+        else g = sigmoid_t(fma_t(uu, uu, L.ul));
         d = fma_t(g, mu, -eo);                                    // :408
         skip = abs_t(d) < eps;                                    // :410-413
         en = skip ? eo : add_t(eo, d);                            // :431
@@ -240,7 +249,8 @@ struct SmemView {
 
 template <typename U>
 __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char* smem, int4* rowmeta, int4* panelmeta,
-                                              uint64_t* full, uint64_t* empty, int r0, int pan0, int NP, int lane) {
+                                              uint64_t* full, uint64_t* empty, int r0, int pan0, int NP, int lane,
+                                              int* rowbase = nullptr, int4* panelmeta2 = nullptr) {
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int ES = (int)sizeof(U);
     const int NST = p.nst;
@@ -262,26 +272,38 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
         int c = 0;
         if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
         const int need_next = (v + 1 < NP) ? p.panel_need[pan0 + v + 1] : 0;   // what the chain needs before panel v+1
-        trace_ev(p, lane, 9, 0, v);
-        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-        trace_ev(p, lane, 9, 1, v);
+        // everything that does not touch shared memory comes before the wait: the TMA is issued a few
+        // instructions after the stage is released
         int vs = 0x7fffffff, ve = 0;
+        int lo = 0, hi = 0x7fffffff;                 // vectors [lo, hi) are stored by EVERY row of the panel
+        int4 m = make_int4(0, 0, 0, 0);
         if (lane < P) {
             const int nv = (int)(o1 - o0) / EPV;
             const int vs_r = c / EPV;
-            int4 m;
             m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
             m.y = vs_r; m.z = vs_r + nv; m.w = need_next;
-            rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
             if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
+            lo = vs_r; hi = vs_r + nv;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             vs = min(vs, __shfl_xor_sync(0xffffffffu, vs, o));
             ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
+            lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = min(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
         const uint32_t bytes = (uint32_t)((oend - obase) * ES);
-        if (lane == 0) panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
+        trace_ev(p, lane, 9, 0, v);
+        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+        trace_ev(p, lane, 9, 1, v);
+        if (lane < P) {
+            rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
+            if (rowbase != nullptr) rowbase[(rs - r0 + lane) & (RR - 1)] = m.x;
+        }
+        if (lane == 0) {
+            panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
+            if (panelmeta2 != nullptr) panelmeta2[s] = make_int4(lo, hi, 0, 0);
+        }
         __syncwarp();
         if (lane == 0) {
             if (bytes > 0) {
@@ -302,7 +324,8 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
 }
 
 // NA / NC: number of bulk warps that publish a_prog / c_prog (and dot partials)
-template <typename T, typename Model, int NA, int NC>
+// NW: warps that only publish a progress counter the chain waits on like an A counter (prog layout: A | W | C)
+template <typename T, typename Model, int NA, int NC, int NW = 0>
 __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
                                            const SmemView<T>& sm, int r0, int B, int pan0, int NP, int lane) {
     const int NST = p.nst;
@@ -328,7 +351,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
     for (int u = 0; u < NP; ++u) {
         // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
         trace_ev(p, lane, 8, 0, u);
-        wait_progress<NA, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c, lane);
+        wait_progress<NA + NW, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c, lane);
         trace_ev(p, lane, 8, 1, u);
         const int nrows = (int)lds128(a_panelmeta + s * 16).x;
         need_c = (int)lds128(a_rowmeta + (j0 & (RR - 1)) * 16).w;
@@ -356,21 +379,27 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
                     if (h + i < nrows) w0[i] = lds_t(wr, T());
                     if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_t(wr + 32 * sizeof(T), T());
                 }
+                // one SNP update; lanes other than the row's owner compute with a stale X0 and their result is unused
+                auto one_step = [&](int i) {
+                    T en, d;
+                    bool skip;
+                    typename Model::Out o;
+                    Model::step(L, X0, eo, eps, en, d, skip, o);
+                    const bool mine = (rel == h + i);
+                    Xown = mine ? X0 : Xown;
+                    const T x0n = mine ? X1 : X0;          // the window slides by one column: independent of the shuffle
+                    const T x1n = mine ? T(0) : X1;
+                    const T a = shfl_t(en, (base + h + i) & 31);
+                    X0 = fma_t(w0[i], a, x0n);             // :421 restricted to the window
+                    X1 = fma_t(w1[i], a, x1n);
+                };
+                if (h + 4 <= nrows) {                      // full group: no per-step branches on the serial path
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (h + i < nrows) {
-                        T en, d;
-                        bool skip;
-                        typename Model::Out o;
-                        Model::step(L, X0, eo, eps, en, d, skip, o);
-                        const bool mine = (rel == h + i);
-                        Xown = mine ? X0 : Xown;
-                        const T a = shfl_t(en, (base + h + i) & 31);
-                        X0 = mine ? X1 : X0;
-                        X1 = mine ? T(0) : X1;
-                        X0 = fma_t(w0[i], a, X0);              // :421 restricted to the window
-                        X1 = fma_t(w1[i], a, X1);
-                    }
+                    for (int i = 0; i < 4; ++i) one_step(i);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (h + i < nrows) one_step(i);
                 }
             }
         }
@@ -418,6 +447,106 @@ __device__ __forceinline__ void window_row(unsigned char* smem, const int4* rowm
         T v = T(0);
         if (col < cut && col / EPV >= m.y && col / EPV < m.z) v = ld_elem<T, U>(smem + m.x + col * ES);
         wwin[(jl & (RR - 1)) * WW + kk] = v;
+    }
+}
+
+// Window coefficients of a whole landed panel, split over NP_ warps (part = 0..NP_-1).  Branch-free straight-line
+// code with independent loads (an element outside the row's stored range or beyond the cut reads the "code 0"
+// constant at zaddr): a warp-item is either (row r, kk = lane) -- P of those -- or (rows 2 i + (lane >> 4),
+// kk = 32 + (lane & 15)) -- ceil(P / 2) of those; part `part` takes items part, part + NP_, ...
+template <typename U> __device__ __forceinline__ float lds_code(uint32_t addr);
+template <> __device__ __forceinline__ float lds_code<int8_t>(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (float)((int)v - 128);
+}
+template <> __device__ __forceinline__ float lds_code<int16_t>(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (float)((int)v - 32768);
+}
+template <> __device__ __forceinline__ float lds_code<float>(uint32_t addr) { return lds_t(addr, float()); }
+
+template <typename U, int NP_>
+__device__ __forceinline__ void window_panel(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, uint32_t zaddr,
+                                             int jl0, int P, int part, int lane) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+    constexpr int NIT = (PMAX + PMAX / 2 + NP_ - 1) / NP_;
+    static_assert(WW == 48, "window_panel assumes 32 + 16 coefficients per row");
+    const int nit = P + (P + 1) / 2;
+    int jl[NIT], kk[NIT];
+    bool ok[NIT];
+    uint4 m[NIT];
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+        const int i = part + q * NP_;
+        const bool first = i < P;
+        const int r = first ? i : 2 * (i - P) + (lane >> 4);
+        kk[q] = first ? lane : 32 + (lane & 15);
+        ok[q] = (i < nit) && (r < P);
+        jl[q] = jl0 + (ok[q] ? r : 0);
+        m[q] = lds128(a_rowmeta + (uint32_t)(jl[q] & (RR - 1)) * 16u);
+    }
+    float v[NIT];
+#pragma unroll
+    for (int q = 0; q < NIT; ++q) {
+        // block-local indices are non-negative: unsigned shifts, and plain & instead of && (no lazy-evaluation branches)
+        const uint32_t cut = (((uint32_t)jl[q] + WIN + EPV - 1) / EPV) * EPV;
+        const uint32_t col = (uint32_t)jl[q] + 1u + (uint32_t)kk[q];
+        const uint32_t cv = col / EPV;
+        const bool in = ok[q] & (col < cut) & (cv >= m[q].y) & (cv < m[q].z);
+        v[q] = lds_code<U>(in ? sbase + m[q].x + col * ES : zaddr);
+    }
+#pragma unroll
+    for (int q = 0; q < NIT; ++q)
+        if (ok[q]) sts_t(a_wwin + (uint32_t)((jl[q] & (RR - 1)) * WW + kk[q]) * 4u, v[q]);
+}
+
+// int8 LD: the same job four coefficients at a time.  Lane l < 24 of part `part` takes word w = l % 12 (columns
+// j + 1 + 4 w .. + 3) of row 2 part + l / 12 (+ 8 for the second half of a 16-row panel): two aligned 32-bit loads
+// and a byte funnel fetch the four codes, one 128-bit store writes the four coefficients.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int NP_>
+__device__ __forceinline__ void window_panel_i8(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, int jl0, int P,
+                                                int part, int lane) {
+    static_assert(WW == 48 && NP_ == 4 && PMAX == 16, "window_panel_i8: 12 words per row, 2 rows per part and pass");
+    const uint32_t w = (uint32_t)lane % 12u, rsub = (uint32_t)lane / 12u;
+    uint4 m[2];
+    uint32_t jl[2];
+    bool ok[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t r = 2u * (uint32_t)part + rsub + 8u * it;
+        ok[it] = (lane < 24) & (r < (uint32_t)P);
+        jl[it] = (uint32_t)jl0 + (ok[it] ? r : 0u);
+        m[it] = lds128(a_rowmeta + (jl[it] & (RR - 1)) * 16u);
+    }
+    uint32_t lo[2], hi[2], a[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        a[it] = sbase + m[it].x + jl[it] + 1u + 4u * w;                 // byte address of the first of the four codes
+        lo[it] = lds_u32(a[it] & ~3u);
+        hi[it] = lds_u32((a[it] & ~3u) + 4u);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t word = __byte_perm(lo[it], hi[it], 0x3210u + 0x1111u * (a[it] & 3u));
+        const uint32_t col0 = jl[it] + 1u + 4u * w;
+        const uint32_t cut = ((jl[it] + WIN + 15u) / 16u) * 16u;
+        const uint32_t lim = min(cut, m[it].z * 16u), beg = m[it].y * 16u;     // stored and chain-owned: [beg, lim)
+        float2 p0, p1;
+        VecOps<float, int8_t>::pairs(word, p0, p1);
+        uint4 o;
+        o.x = (col0 >= beg) & (col0 < lim) ? __float_as_uint(p0.x) : 0u;
+        o.y = (col0 + 1u >= beg) & (col0 + 1u < lim) ? __float_as_uint(p0.y) : 0u;
+        o.z = (col0 + 2u >= beg) & (col0 + 2u < lim) ? __float_as_uint(p1.x) : 0u;
+        o.w = (col0 + 3u >= beg) & (col0 + 3u < lim) ? __float_as_uint(p1.y) : 0u;
+        if (ok[it]) sts128(a_wwin + ((jl[it] & (RR - 1)) * WW + 4u * w) * 4u, o);
     }
 }
 

@@ -19,23 +19,12 @@ namespace vb {
 
 constexpr int NAW = 4;                    // A warps
 constexpr int NCW = 4;                    // C warps
-// 11 warps per CTA.  Warps are dealt to the four SM sub-partitions round-robin (warp % 4), so warps 1, 5, 9 share
-// one scheduler: the latency-critical chain warp (1) and the producer (5) get it to themselves (9 exits at once);
-// the eight bulk warps run on the other three schedulers and cannot steal the chain's issue slots or pipes.
-#ifndef VB_FAST_ISOLATE
-#define VB_FAST_ISOLATE 0       // measured on B200 (C2 workload): 1.103 ms shared vs 1.135 ms isolated
-#endif
-#if VB_FAST_ISOLATE
-constexpr int FAST_WARPS = 11;
-constexpr int FAST_CHAIN_WARP = 1, FAST_PRODUCER_WARP = 5, FAST_IDLE_WARP = 9;
-__device__ __forceinline__ int fast_a_index(int warp) { return warp == 0 ? 0 : (warp >= 2 && warp <= 4) ? warp - 1 : -1; }
-__device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 6 && warp <= 8) ? warp - 6 : warp == 10 ? 3 : -1; }
-#else
+constexpr int NWW = 0;                    // progress-only warps between the A and C counters (none)
+// 10 warps per CTA: 0-3 A, 4-7 C, 8 producer, 9 chain (highest warp id).
 constexpr int FAST_WARPS = 10;
-constexpr int FAST_CHAIN_WARP = 9, FAST_PRODUCER_WARP = 8, FAST_IDLE_WARP = -1;
+constexpr int FAST_CHAIN_WARP = 9, FAST_PRODUCER_WARP = 8;
 __device__ __forceinline__ int fast_a_index(int warp) { return warp < 4 ? warp : -1; }
 __device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && warp < 8) ? warp - 4 : -1; }
-#endif
 constexpr int GT = 128;                   // threads per bulk group
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
@@ -43,7 +32,7 @@ constexpr int HP = 258;                   // entries of the fixed-point prefix s
 constexpr int NLIMB_MAX = 4;
 
 struct FastLayout {
-    uint32_t stages, rowmeta, panelmeta, partial, alpha, wwin, fring, hc, zero, red, bars, counters, total;
+    uint32_t stages, rowmeta, panelmeta, panelmeta2, rowbase, partial, alpha, wwin, fring, hc, zero, red, bars, counters, total;
 };
 inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     FastLayout L;
@@ -51,6 +40,8 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     L.stages = o;    o += (uint32_t)nst * (uint32_t)stage_bytes;       o = align128(o);
     L.rowmeta = o;   o += RR * (uint32_t)sizeof(int4);
     L.panelmeta = o; o += NST_MAX * (uint32_t)sizeof(int4);
+    L.panelmeta2 = o; o += NST_MAX * (uint32_t)sizeof(int4);       // {lo, hi}: vectors stored by every row of the panel
+    L.rowbase = o;   o += RR * 4;                                  // rowmeta[].x alone: one LDS.128 = four rows
     L.partial = o;   o += NAW * RR * 4;
     L.alpha = o;     o += RR * 4;
     L.wwin = o;      o += RR * WW * 4;
@@ -59,9 +50,25 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     L.zero = o;      o += 32;
     L.red = L.partial;                   // prologue scratch, dead before the first partial is written
     L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
-    L.counters = o;  o += (NAW + NCW) * (uint32_t)sizeof(uint32_t);
+    L.counters = o;  o += (NAW + NWW + NCW) * (uint32_t)sizeof(uint32_t);
     L.total = o;
     return L;
+}
+
+// Static column ownership of the bulk warps.  The 4 NVT tiles of 32 LD vectors (tile i = vectors [32 i, 32 i + 32))
+// are dealt to the four warps of a group boustrophedon-wise: warp w owns tiles w, 7 - w, 8 + w, 15 - w, ...  Row j
+// only touches the vectors >= j / EPV, so a tile's work grows with its index; the serpentine deal gives every warp
+// (= every SM sub-partition) the same share of the triangle, where the plain deal (tile 4 c + w) loads the
+// scheduler of warp 3 with 11/8 of the average.
+#ifndef VB_FAST_BALANCE
+#define VB_FAST_BALANCE 1
+#endif
+__device__ __forceinline__ int fast_tile(int w, int c) {
+#if VB_FAST_BALANCE
+    return 4 * c + ((c & 1) ? 3 - w : w);
+#else
+    return 4 * c + w;
+#endif
 }
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // sum_b u8(a.b) * s8(b.b) + c
@@ -103,7 +110,6 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
     const int ai = fast_a_index(warp), ci = fast_c_index(warp);
-    const int ta = ai * WARP + lane;                     // 0..127 inside the A group (when ai >= 0)
     const int blk = p.blk_order[blockIdx.x];
     const int r0 = p.blk_row[blk], r1 = p.blk_row[blk + 1];
     const int B = r1 - r0;
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     // ---- prologue ----------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); mbar_init(&sm.cdone[s], 1); }
-        for (int w = 0; w < NAW + NCW; ++w) sm.prog[w] = 0;
+        for (int w = 0; w < NAW + NWW + NCW; ++w) sm.prog[w] = 0;
         fence_mbar_init();
     }
     for (int i = tid; i < FR; i += blockDim.x) fring[i] = 0.f;
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
         if (ai >= 0) {
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
-                const int v = ta + GT * c;
+                const int v = 32 * fast_tile(ai, c) + lane;
                 long long qsum = 0;
 #pragma unroll
                 for (int l = 0; l < NLIMB; ++l)
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
             for (int c = 0; c < NVT; ++c) {
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    const int col = (ta + GT * c) * EPV + e;
+                    const int col = (32 * fast_tile(ai, c) + lane) * EPV + e;
                     es[c][e] = (col < B) ? sa.eta[r0 + col] : 0.f;
                 }
             }
@@ -195,98 +201,142 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     }
     __syncthreads();
 
-    if (warp == FAST_IDLE_WARP) return;
     if (warp == FAST_PRODUCER_WARP) {
-        producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane);
+        producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
+                         reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
     } else if (warp == FAST_CHAIN_WARP) {
-        chain_role<T, Model, NAW, NCW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
+        chain_role<T, Model, NAW, NCW, NWW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else if (ai >= 0) {
         // =============================== A: backward dots =====================================
-        // Branch-free inner loop: a (row, vector) pair outside the row's range reads a 16-byte zero vector.
+        // Per panel every owned tile is classified (warp-uniform): dead (no row of the panel stores it), interior
+        // (every row stores all of it: address = row base + own offset, no predicates) or boundary (the general,
+        // branch-free form: a (row, vector) pair outside the row's range reads a 16-byte zero vector).
         const int wa = ai;
-        const int t = ta;                                    // 0..127
         const uint32_t zaddr = DP4A ? zaddr_raw : zaddr_code;
+        const uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2;
+        int vown[NVT];
+        uint32_t vaddr[NVT];
+#pragma unroll
+        for (int c = 0; c < NVT; ++c) { vown[c] = 32 * fast_tile(wa, c) + lane; vaddr[c] = sbase + (uint32_t)vown[c] * 16u; }
         int s = 0, k = 0;
         for (int u = 0; u < NP; ++u) {
             trace_ev(p, lane, wa, 0, u);
             mbar_wait(&sm.full[s], k & 1);
             trace_ev(p, lane, wa, 1, u);
             const int4 pm = sm.panelmeta[s];
-            const int P = pm.x, jl0 = pm.w;
-            for (int r = wa; r < P; r += NAW) window_row<T, U>(smem, sm.rowmeta, sm.wwin, jl0 + r, lane);
+            const uint4 pm2 = lds128(a_pm2 + s * 16);
+            const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
+            const int lo_all = (int)pm2.x, hi_all = (int)pm2.y;
+            if constexpr (DP4A) window_panel_i8<NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, jl0, P, wa, lane);
+            else window_panel<U, NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, zaddr_code, jl0, P, wa, lane);
+            trace_ev(p, lane, wa, 3, u);
+            const bool quad = ((jl0 | P) & 3) == 0;
+            bool live[NVT], inter[NVT];
+            bool anyl = false, anyb = false;
+#pragma unroll
+            for (int c = 0; c < NVT; ++c) {
+                const int tb = 32 * fast_tile(wa, c);
+                live[c] = (tb + 32 > vmin) && (tb < vmax);
+                inter[c] = quad && (tb >= lo_all) && (tb + 32 <= hi_all);
+                anyl |= live[c];
+                anyb |= live[c] && !inter[c];
+            }
             [[maybe_unused]] int dig[DP4A ? NLIMB : 1];       // lane r: digit totals of row r of the panel
 #pragma unroll
             for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) dig[l] = 0;
+            if (!anyl) {
+                if constexpr (!DP4A) {
+                    if (lane < P) sm.partial[wa * RR + ((jl0 + lane) & (RR - 1))] = 0.f;
+                }
+            } else {
 #pragma unroll 1
-            for (int rg = 0; rg < P; rg += 4) {
-                const int nv = min(4, P - rg);
-                int mx[4], my[4], mz[4];
+                for (int rg = 0; rg < P; rg += 4) {
+                    const int nv = min(4, P - rg);
+                    int mx[4];
+                    [[maybe_unused]] int my[4], mz[4];
+                    if (anyb) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    mx[r] = 0; my[r] = 0; mz[r] = 0;
-                    if (r < nv) {
-                        const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
-                        mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                        for (int r = 0; r < 4; ++r) {
+                            mx[r] = 0; my[r] = 0; mz[r] = 0;
+                            if (r < nv) {
+                                const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
+                                mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                            }
+                        }
+                    } else {
+                        const uint4 b = lds128(a_rowbase + (uint32_t)((jl0 + rg) & (RR - 1)) * 4u);
+                        mx[0] = (int)b.x; mx[1] = (int)b.y; mx[2] = (int)b.z; mx[3] = (int)b.w;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { my[r] = 0; mz[r] = 0; }
                     }
-                }
-                [[maybe_unused]] int acc[4][DP4A ? NLIMB : 1];
-                [[maybe_unused]] typename Pk<T>::acc_t acc2[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    acc2[r] = Pk<T>::zero();
-#pragma unroll
-                    for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) acc[r][l] = 0;
-                }
-#pragma unroll
-                for (int c = 0; c < NVT; ++c) {
-                    const int v = t + GT * c;
-                    uint32_t ad[4];
-                    bool any = false;
+                    [[maybe_unused]] int acc[4][DP4A ? NLIMB : 1];
+                    [[maybe_unused]] typename Pk<T>::acc_t acc2[4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const bool in = (v >= my[r]) && (v < mz[r]);
-                        any |= in;
-                        ad[r] = in ? sbase + (uint32_t)(mx[r] + v * 16) : zaddr;
+                        acc2[r] = Pk<T>::zero();
+#pragma unroll
+                        for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) acc[r][l] = 0;
                     }
-                    if (!__any_sync(0xffffffffu, any)) continue;         // no lane of the warp owns a live vector here
-                    uint4 cv[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+                    for (int c = 0; c < NVT; ++c) {
+                        if (!live[c]) continue;
+                        uint32_t ad[4];
+                        if (inter[c]) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        if constexpr (DP4A) {
+                            for (int r = 0; r < 4; ++r) ad[r] = vaddr[c] + (uint32_t)mx[r];
+                        } else {
+                            const int v = vown[c];
+                            bool any = false;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const bool in = (v >= my[r]) && (v < mz[r]);
+                                any |= in;
+                                ad[r] = in ? vaddr[c] + (uint32_t)mx[r] : zaddr;
+                            }
+                            if (!__any_sync(0xffffffffu, any)) continue;     // no lane of the warp owns a live vector here
+                        }
+                        uint4 cv[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if constexpr (DP4A) {
+#pragma unroll
+                                for (int l = 0; l < NLIMB; ++l) {
+                                    int a = acc[r][l];
+                                    a = dp4a_us(cv[r].x, hl[c][l][0], a);
+                                    a = dp4a_us(cv[r].y, hl[c][l][1], a);
+                                    a = dp4a_us(cv[r].z, hl[c][l][2], a);
+                                    a = dp4a_us(cv[r].w, hl[c][l][3], a);
+                                    acc[r][l] = a;
+                                }
+                            } else {
+                                VecOps<T, U>::dot(cv[r], es[c], acc2[r]);
+                            }
+                        }
+                    }
+                    if (rg == 0) trace_ev(p, lane, wa, 4, u);
+                    if constexpr (DP4A) {
+                        // exact integer totals: one REDUX per (row, digit); lane (rg + r) keeps the digits of row rg + r
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
 #pragma unroll
                             for (int l = 0; l < NLIMB; ++l) {
-                                int a = acc[r][l];
-                                a = dp4a_us(cv[r].x, hl[c][l][0], a);
-                                a = dp4a_us(cv[r].y, hl[c][l][1], a);
-                                a = dp4a_us(cv[r].z, hl[c][l][2], a);
-                                a = dp4a_us(cv[r].w, hl[c][l][3], a);
-                                acc[r][l] = a;
+                                const int tot = __reduce_add_sync(0xffffffffu, acc[r][l]);
+                                if (lane == rg + r) dig[l] = tot;
                             }
-                        } else {
-                            VecOps<T, U>::dot(cv[r], es[c], acc2[r]);
                         }
+                    } else {
+                        T acc1[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc1[r] = Pk<T>::sum(acc2[r]);
+                        const int rr = warp_reduce4(acc1, lane);
+                        if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc1[0];
                     }
-                }
-                if constexpr (DP4A) {
-                    // exact integer totals: one REDUX per (row, digit); lane (rg + r) keeps the digits of row rg + r
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                        for (int l = 0; l < NLIMB; ++l) {
-                            const int tot = __reduce_add_sync(0xffffffffu, acc[r][l]);
-                            if (lane == rg + r) dig[l] = tot;
-                        }
-                    }
-                } else {
-                    T acc1[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc1[r] = Pk<T>::sum(acc2[r]);
-                    const int rr = warp_reduce4(acc1, lane);
-                    if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc1[0];
+                    if (rg == 0) trace_ev(p, lane, wa, 5, u);
                 }
             }
+            trace_ev(p, lane, wa, 6, u);
             if constexpr (DP4A) {
                 // lane r < P: recombine the digits of row r in int64.  sum_b u8 * digit = sum code * digit +
                 // 128 * sum digit over the row's packed range; the range term (128 * sum of Q over the range, from
@@ -310,7 +360,11 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     } else {
         // =============================== C: forward axpy ======================================
         const int wc = ci;
-        const int t = ci * WARP + lane;                      // 0..127
+        const uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2, a_alpha = sbase + FL.alpha;
+        int vown[NVT];
+        uint32_t vaddr[NVT];
+#pragma unroll
+        for (int c = 0; c < NVT; ++c) { vown[c] = 32 * fast_tile(wc, c) + lane; vaddr[c] = sbase + (uint32_t)vown[c] * 16u; }
         float f[NVT][EPV];
 #pragma unroll
         for (int c = 0; c < NVT; ++c)
@@ -322,46 +376,82 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
             mbar_wait(&sm.cdone[s], k & 1);
             trace_ev(p, lane, 4 + wc, 4, v);
             const int4 pm = sm.panelmeta[s];
-            const int Pc = pm.x, jl0 = pm.w;
+            const uint4 pm2 = lds128(a_pm2 + s * 16);
+            const int Pc = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
+            const int cut0 = (jl0 + WIN + EPV - 1) / EPV;                // first vector the bulk owns of the first row
+            const int cutl = (jl0 + Pc - 1 + WIN + EPV - 1) / EPV;       // ... of the last row
+            const int lo_c = max((int)pm2.x, cutl), hi_c = (int)pm2.y;
+            const bool quad = ((jl0 | Pc) & 3) == 0;
+            bool live[NVT], inter[NVT];
+            bool anyl = false, anyb = false;
+#pragma unroll
+            for (int c = 0; c < NVT; ++c) {
+                const int tb = 32 * fast_tile(wc, c);
+                live[c] = (tb + 32 > max(vmin, cut0)) && (tb < vmax);
+                inter[c] = quad && (tb >= lo_c) && (tb + 32 <= hi_c);
+                anyl |= live[c];
+                anyb |= live[c] && !inter[c];
+            }
+            if (anyl) {
 #pragma unroll 1
-            for (int rg = 0; rg < Pc; rg += 4) {
-                const int nv = min(4, Pc - rg);
-                int mx[4], my[4], mz[4];
-                T al[4];
+                for (int rg = 0; rg < Pc; rg += 4) {
+                    const int nv = min(4, Pc - rg);
+                    int mx[4];
+                    [[maybe_unused]] int my[4], mz[4];
+                    T al[4];
+                    if (anyb) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
-                    if (r < nv) {
-                        const int jl = jl0 + rg + r;
-                        const int4 m = sm.rowmeta[jl & (RR - 1)];
-                        mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
-                        al[r] = sm.alpha[jl & (RR - 1)];
+                        for (int r = 0; r < 4; ++r) {
+                            mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
+                            if (r < nv) {
+                                const int jl = jl0 + rg + r;
+                                const int4 m = sm.rowmeta[jl & (RR - 1)];
+                                mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
+                                al[r] = sm.alpha[jl & (RR - 1)];
+                            }
+                        }
+                    } else {
+                        const uint32_t slot = (uint32_t)((jl0 + rg) & (RR - 1)) * 4u;
+                        const uint4 b = lds128(a_rowbase + slot);
+                        const uint4 a4 = lds128(a_alpha + slot);
+                        mx[0] = (int)b.x; mx[1] = (int)b.y; mx[2] = (int)b.z; mx[3] = (int)b.w;
+                        al[0] = __uint_as_float(a4.x); al[1] = __uint_as_float(a4.y);
+                        al[2] = __uint_as_float(a4.z); al[3] = __uint_as_float(a4.w);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { my[r] = 0; mz[r] = 0; }
                     }
-                }
 #pragma unroll
-                for (int c = 0; c < NVT; ++c) {
-                    const int vv = t + GT * c;
-                    uint32_t ad[4];
-                    bool any = false;
+                    for (int c = 0; c < NVT; ++c) {
+                        if (!live[c]) continue;
+                        uint32_t ad[4];
+                        if (inter[c]) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const bool in = (vv >= my[r]) && (vv < mz[r]);
-                        any |= in;
-                        ad[r] = in ? sbase + (uint32_t)(mx[r] + vv * 16) : zaddr_code;
+                            for (int r = 0; r < 4; ++r) ad[r] = vaddr[c] + (uint32_t)mx[r];
+                        } else {
+                            const int vv = vown[c];
+                            bool any = false;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const bool in = (vv >= my[r]) && (vv < mz[r]);
+                                any |= in;
+                                ad[r] = in ? vaddr[c] + (uint32_t)mx[r] : zaddr_code;
+                            }
+                            if (!__any_sync(0xffffffffu, any)) continue;
+                        }
+                        uint4 cv[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) VecOps<T, U>::axpy(cv[r], al[r], f[c]);
                     }
-                    if (!__any_sync(0xffffffffu, any)) continue;
-                    uint4 cv[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) VecOps<T, U>::axpy(cv[r], al[r], f[c]);
                 }
             }
+            trace_ev(p, lane, 4 + wc, 6, v);
             // columns below cut(first row after the panel) are complete: publish them for the chain
             const int newpub = min(nvec, (jl0 + Pc + WIN + EPV - 1) / EPV);
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
-                const int vv = t + GT * c;
+                const int vv = vown[c];
                 if (vv >= pubvec && vv < newpub) {
 #pragma unroll
                     for (int e = 0; e < EPV; ++e) fring[(vv * EPV + e) & (FR - 1)] = f[c][e];
@@ -370,7 +460,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
             pubvec = max(pubvec, newpub);
             __syncwarp();
             if (lane == 0) {
-                st_release(&sm.prog[NAW + wc], (uint32_t)(v + 1));
+                st_release(&sm.prog[NAW + NWW + wc], (uint32_t)(v + 1));
                 mbar_arrive(&sm.empty[s]);
             }
             trace_ev(p, lane, 4 + wc, 5, v);
