@@ -4,7 +4,7 @@ import numpy as np
 NP_ = 4096
 a = np.fromfile(sys.argv[1], dtype=np.uint64).astype(np.int64).reshape(-1, 8, NP_)
 t0 = a[a > 0].min()
-fast = a[4, 4].any() and not a[0, 4].any()          # fast kernel: warps 0-3 only A, 4-7 only C
+fast = True
 AW = range(4) if fast else range(8)
 CW = range(4, 8) if fast else range(8)
 def series(r, e):
@@ -47,6 +47,11 @@ if A3max:
 def perwarp(w, e0, e1, lo, hi):
     x, y = series(w, e0), series(w, e1)
     return avg(x, y, lo, hi)
+print("producer: top->prefetch issued->meta+shuffles(ev0)->gates(ev1)->meta stored(ev5)->tma issued(ev2)->released(ev6)->next top")
+for a_, b_ in ((q[0], q[2]), (q[2], q[4])):
+    P3, P4, P5, P6 = series(9, 3), series(9, 4), series(9, 5), series(9, 6)
+    nxt = {k - 1: v for k, v in P3.items()}
+    print("   ", " ".join(f"{avg(x, y, a_, b_):7.0f}" for x, y in ((P3, P4), (P4, PW0), (PW0, PW1), (PW1, P5), (P5, P), (P, P6), (P6, nxt))))
 print("per-warp phase durations (first half | second half of the block)")
 for w in AW:
     print(f"  A{w}: wait-full " + " | ".join(f"{perwarp(w, 0, 1, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +

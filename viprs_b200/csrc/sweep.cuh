@@ -30,6 +30,8 @@
 // hardware-suspending try_wait, plus per-bulk-warp release/acquire progress counters a_prog / c_prog that
 // only the chain warp polls.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vb {
@@ -101,6 +103,7 @@ struct SlabModel {
         T* var_gamma; T* var_mu; T dq;
     };
     static constexpr bool kHeavy = false;
+    static constexpr bool kDualGroups = true;      // chain: separate branch-free code for full 4-step groups
     struct Raw { T beta, mm, sv, ul; };
     struct Lane { T c0, c1, a0, a1, ul; };      // mu = c1 X + c0 ;  sqrt(tau/2) mu = a1 X + a0
     struct Out { T mu, g; };
@@ -147,6 +150,8 @@ struct MixModel {
         T* var_gamma; T* var_mu; T dq; int K;
     };
     static constexpr bool kHeavy = (KMAX > 4);       // register-hungry: always one CTA per SM
+    static constexpr bool kDualGroups = false;       // the step is large: a second inlined copy costs more (instruction
+                                                     // cache) than its per-step branches (measured on the C4 workload)
     struct Raw { T beta, lnp; T mm[KMAX], sv[KMAX], ul[KMAX]; };
     struct Lane { T beta, lnp, dq; T mm[KMAX], sv[KMAX], ul[KMAX]; int K; };
     struct Out { T mu[KMAX], g[KMAX]; };
@@ -245,7 +250,28 @@ struct SmemView {
     uint32_t* prog;     // a_prog[NA] | c_prog[NC]
     const T* fsrc;      // forward accumulator as the chain reads it: fsrc[col & fmask]
     int fmask;
+    // register-resident kernel only: panelmeta / cdone are rings indexed by panel (u & (PMR - 1)) instead of by TMA
+    // stage (the stage is recycled as soon as the A warps are done with it), the chain publishes the rows it has
+    // finished, and never runs more than PMR - 2 panels ahead of the slowest C warp
+    bool by_panel = false;
+    uint32_t* chain_rows = nullptr;
 };
+constexpr int PMR = 16;       // panel-indexed rings (power of two)
+constexpr int CR = 128;       // per-row ring read by the C warps of the register-resident kernel (power of two)
+
+// window coefficient storage: the state type, or int16 (integer LD codes are exact in it) to save shared memory
+template <typename W> __device__ __forceinline__ float lds_w(uint32_t addr);
+template <> __device__ __forceinline__ float lds_w<float>(uint32_t addr) { return lds_t(addr, float()); }
+template <> __device__ __forceinline__ float lds_w<int16_t>(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (float)v;
+}
+template <typename W> __device__ __forceinline__ void sts_w(uint32_t addr, float v);
+template <> __device__ __forceinline__ void sts_w<float>(uint32_t addr, float v) { sts_t(addr, v); }
+template <> __device__ __forceinline__ void sts_w<int16_t>(uint32_t addr, float v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((short)__float2int_rn(v)) : "memory");
+}
 
 template <typename U>
 __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char* smem, int4* rowmeta, int4* panelmeta,
@@ -325,7 +351,7 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
 
 // NA / NC: number of bulk warps that publish a_prog / c_prog (and dot partials)
 // NW: warps that only publish a progress counter the chain waits on like an A counter (prog layout: A | W | C)
-template <typename T, typename Model, int NA, int NC, int NW = 0>
+template <typename T, typename Model, int NA, int NC, int NW = 0, typename W = T>
 __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
                                            const SmemView<T>& sm, int r0, int B, int pan0, int NP, int lane) {
     const int NST = p.nst;
@@ -351,9 +377,11 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
     for (int u = 0; u < NP; ++u) {
         // one batch = one row panel (1..16 rows): rows [j0, j0 + nrows) of the block
         trace_ev(p, lane, 8, 0, u);
+        const int pidx = sm.by_panel ? (u & (PMR - 1)) : s;
+        if (sm.by_panel) need_c = max(need_c, u - (PMR - 2));       // keeps the panel-indexed cdone ring unambiguous
         wait_progress<NA + NW, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c, lane);
         trace_ev(p, lane, 8, 1, u);
-        const int nrows = (int)lds128(a_panelmeta + s * 16).x;
+        const int nrows = (int)lds128(a_panelmeta + pidx * 16).x;
         need_c = (int)lds128(a_rowmeta + (j0 & (RR - 1)) * 16).w;
         const int base = j0 & 31;
         const int rel = (lane - base) & 31;
@@ -374,10 +402,15 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int k0 = (rel - (h + i) - 1) & 31;       // window slot of the lane's X0 column at this step
-                    const uint32_t wr = a_wwin + (uint32_t)((((j0 + h + i) & (RR - 1)) * WW + k0) * sizeof(T));
+                    const uint32_t wr = a_wwin + (uint32_t)((((j0 + h + i) & (RR - 1)) * WW + k0) * sizeof(W));
                     w0[i] = T(0); w1[i] = T(0);
-                    if (h + i < nrows) w0[i] = lds_t(wr, T());
-                    if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_t(wr + 32 * sizeof(T), T());
+                    if constexpr (std::is_same<W, T>::value) {
+                        if (h + i < nrows) w0[i] = lds_t(wr, T());
+                        if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_t(wr + 32 * sizeof(T), T());
+                    } else {
+                        if (h + i < nrows) w0[i] = lds_w<W>(wr);
+                        if (h + i < nrows && k0 + 32 < WW) w1[i] = lds_w<W>(wr + 32 * sizeof(W));
+                    }
                 }
                 // one SNP update; lanes other than the row's owner compute with a stale X0 and their result is unused
                 auto one_step = [&](int i) {
@@ -393,7 +426,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
                     X0 = fma_t(w0[i], a, x0n);             // :421 restricted to the window
                     X1 = fma_t(w1[i], a, x1n);
                 };
-                if (h + 4 <= nrows) {                      // full group: no per-step branches on the serial path
+                if (Model::kDualGroups && h + 4 <= nrows) {   // full group: no per-step branches on the serial path
 #pragma unroll
                     for (int i = 0; i < 4; ++i) one_step(i);
                 } else {
@@ -420,7 +453,10 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             sts_t(a_alpha + (uint32_t)(cl & (RR - 1)) * sizeof(T), en);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.cdone[s]);
+        if (lane == 0) {
+            mbar_arrive(&sm.cdone[pidx]);
+            if (sm.chain_rows != nullptr) st_release(sm.chain_rows, (uint32_t)(j0 + nrows));
+        }
         trace_ev(p, lane, 8, 3, u);
         if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; has_pend = false; }
         if (rel < nrows) {
@@ -467,40 +503,45 @@ template <> __device__ __forceinline__ float lds_code<int16_t>(uint32_t addr) {
 }
 template <> __device__ __forceinline__ float lds_code<float>(uint32_t addr) { return lds_t(addr, float()); }
 
-template <typename U, int NP_>
+template <typename U, int NP_, typename W = float>
 __device__ __forceinline__ void window_panel(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, uint32_t zaddr,
                                              int jl0, int P, int part, int lane) {
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int ES = (int)sizeof(U);
     constexpr int NIT = (PMAX + PMAX / 2 + NP_ - 1) / NP_;
+    constexpr int NB = 2;                                  // items in flight per batch
     static_assert(WW == 48, "window_panel assumes 32 + 16 coefficients per row");
     const int nit = P + (P + 1) / 2;
-    int jl[NIT], kk[NIT];
-    bool ok[NIT];
-    uint4 m[NIT];
+#pragma unroll 1
+    for (int q0 = 0; q0 < NIT; q0 += NB) {
+        if (part + q0 * NP_ >= nit) break;                 // warp-uniform
+        int jl[NB], kk[NB];
+        bool ok[NB];
+        uint4 m[NB];
 #pragma unroll
-    for (int q = 0; q < NIT; ++q) {
-        const int i = part + q * NP_;
-        const bool first = i < P;
-        const int r = first ? i : 2 * (i - P) + (lane >> 4);
-        kk[q] = first ? lane : 32 + (lane & 15);
-        ok[q] = (i < nit) && (r < P);
-        jl[q] = jl0 + (ok[q] ? r : 0);
-        m[q] = lds128(a_rowmeta + (uint32_t)(jl[q] & (RR - 1)) * 16u);
+        for (int q = 0; q < NB; ++q) {
+            const int i = part + (q0 + q) * NP_;
+            const bool first = i < P;
+            const int r = first ? i : 2 * (i - P) + (lane >> 4);
+            kk[q] = first ? lane : 32 + (lane & 15);
+            ok[q] = (i < nit) & (r < P);
+            jl[q] = jl0 + (ok[q] ? r : 0);
+            m[q] = lds128(a_rowmeta + (uint32_t)(jl[q] & (RR - 1)) * 16u);
+        }
+        float v[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            // block-local indices are non-negative: unsigned shifts, and plain & instead of && (no lazy-evaluation branches)
+            const uint32_t cut = (((uint32_t)jl[q] + WIN + EPV - 1) / EPV) * EPV;
+            const uint32_t col = (uint32_t)jl[q] + 1u + (uint32_t)kk[q];
+            const uint32_t cv = col / EPV;
+            const bool in = ok[q] & (col < cut) & (cv >= m[q].y) & (cv < m[q].z);
+            v[q] = lds_code<U>(in ? sbase + m[q].x + col * ES : zaddr);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            if (ok[q]) sts_w<W>(a_wwin + (uint32_t)((jl[q] & (RR - 1)) * WW + kk[q]) * (uint32_t)sizeof(W), v[q]);
     }
-    float v[NIT];
-#pragma unroll
-    for (int q = 0; q < NIT; ++q) {
-        // block-local indices are non-negative: unsigned shifts, and plain & instead of && (no lazy-evaluation branches)
-        const uint32_t cut = (((uint32_t)jl[q] + WIN + EPV - 1) / EPV) * EPV;
-        const uint32_t col = (uint32_t)jl[q] + 1u + (uint32_t)kk[q];
-        const uint32_t cv = col / EPV;
-        const bool in = ok[q] & (col < cut) & (cv >= m[q].y) & (cv < m[q].z);
-        v[q] = lds_code<U>(in ? sbase + m[q].x + col * ES : zaddr);
-    }
-#pragma unroll
-    for (int q = 0; q < NIT; ++q)
-        if (ok[q]) sts_t(a_wwin + (uint32_t)((jl[q] & (RR - 1)) * WW + kk[q]) * 4u, v[q]);
 }
 
 // int8 LD: the same job four coefficients at a time.  Lane l < 24 of part `part` takes word w = l % 12 (columns
@@ -511,42 +552,45 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-template <int NP_>
+template <int NP_, typename W = float>
 __device__ __forceinline__ void window_panel_i8(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, int jl0, int P,
                                                 int part, int lane) {
     static_assert(WW == 48 && NP_ == 4 && PMAX == 16, "window_panel_i8: 12 words per row, 2 rows per part and pass");
     const uint32_t w = (uint32_t)lane % 12u, rsub = (uint32_t)lane / 12u;
-    uint4 m[2];
-    uint32_t jl[2];
-    bool ok[2];
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < 2; ++it) {
+        if (8u * it + 2u * (uint32_t)part >= (uint32_t)P) break;            // warp-uniform
         const uint32_t r = 2u * (uint32_t)part + rsub + 8u * it;
-        ok[it] = (lane < 24) & (r < (uint32_t)P);
-        jl[it] = (uint32_t)jl0 + (ok[it] ? r : 0u);
-        m[it] = lds128(a_rowmeta + (jl[it] & (RR - 1)) * 16u);
-    }
-    uint32_t lo[2], hi[2], a[2];
+        const bool ok = (lane < 24) & (r < (uint32_t)P);
+        const uint32_t jl = (uint32_t)jl0 + (ok ? r : 0u);
+        const uint4 m = lds128(a_rowmeta + (jl & (RR - 1)) * 16u);
+        const uint32_t a = sbase + m.x + jl + 1u + 4u * w;                  // byte address of the first of the four codes
+        const uint32_t lo = lds_u32(a & ~3u);
+        const uint32_t hi = lds_u32((a & ~3u) + 4u);
+        const uint32_t word = __byte_perm(lo, hi, 0x3210u + 0x1111u * (a & 3u));
+        const uint32_t col0 = jl + 1u + 4u * w;
+        const uint32_t cut = ((jl + WIN + 15u) / 16u) * 16u;
+        const uint32_t lim = min(cut, m.z * 16u), beg = m.y * 16u;          // stored and chain-owned: [beg, lim)
+        if constexpr (std::is_same<W, float>::value) {
+            float2 p0, p1;
+            VecOps<float, int8_t>::pairs(word, p0, p1);
+            uint4 o;
+            o.x = (col0 >= beg) & (col0 < lim) ? __float_as_uint(p0.x) : 0u;
+            o.y = (col0 + 1u >= beg) & (col0 + 1u < lim) ? __float_as_uint(p0.y) : 0u;
+            o.z = (col0 + 2u >= beg) & (col0 + 2u < lim) ? __float_as_uint(p1.x) : 0u;
+            o.w = (col0 + 3u >= beg) & (col0 + 3u < lim) ? __float_as_uint(p1.y) : 0u;
+            if (ok) sts128(a_wwin + ((jl & (RR - 1)) * WW + 4u * w) * 4u, o);
+        } else {
+            // int16 storage: code = biased byte - 128, two codes per 32-bit word, one 64-bit store
+            uint32_t c[4];
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        a[it] = sbase + m[it].x + jl[it] + 1u + 4u * w;                 // byte address of the first of the four codes
-        lo[it] = lds_u32(a[it] & ~3u);
-        hi[it] = lds_u32((a[it] & ~3u) + 4u);
-    }
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const uint32_t word = __byte_perm(lo[it], hi[it], 0x3210u + 0x1111u * (a[it] & 3u));
-        const uint32_t col0 = jl[it] + 1u + 4u * w;
-        const uint32_t cut = ((jl[it] + WIN + 15u) / 16u) * 16u;
-        const uint32_t lim = min(cut, m[it].z * 16u), beg = m[it].y * 16u;     // stored and chain-owned: [beg, lim)
-        float2 p0, p1;
-        VecOps<float, int8_t>::pairs(word, p0, p1);
-        uint4 o;
-        o.x = (col0 >= beg) & (col0 < lim) ? __float_as_uint(p0.x) : 0u;
-        o.y = (col0 + 1u >= beg) & (col0 + 1u < lim) ? __float_as_uint(p0.y) : 0u;
-        o.z = (col0 + 2u >= beg) & (col0 + 2u < lim) ? __float_as_uint(p1.x) : 0u;
-        o.w = (col0 + 3u >= beg) & (col0 + 3u < lim) ? __float_as_uint(p1.y) : 0u;
-        if (ok[it]) sts128(a_wwin + ((jl[it] & (RR - 1)) * WW + 4u * w) * 4u, o);
+            for (uint32_t e = 0; e < 4; ++e) {
+                const bool in = (col0 + e >= beg) & (col0 + e < lim);
+                c[e] = in ? (((word >> (8u * e)) & 0xffu) - 128u) & 0xffffu : 0u;
+            }
+            const uint32_t o0 = c[0] | (c[1] << 16), o1 = c[2] | (c[3] << 16);
+            if (ok) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a_wwin + ((jl & (RR - 1)) * WW + 4u * w) * 2u), "r"(o0), "r"(o1) : "memory");
+        }
     }
 }
 

@@ -55,13 +55,13 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     return L;
 }
 
-// Static column ownership of the bulk warps.  The 4 NVT tiles of 32 LD vectors (tile i = vectors [32 i, 32 i + 32))
-// are dealt to the four warps of a group boustrophedon-wise: warp w owns tiles w, 7 - w, 8 + w, 15 - w, ...  Row j
-// only touches the vectors >= j / EPV, so a tile's work grows with its index; the serpentine deal gives every warp
-// (= every SM sub-partition) the same share of the triangle, where the plain deal (tile 4 c + w) loads the
-// scheduler of warp 3 with 11/8 of the average.
+// Static column ownership of the bulk warps: tile i = LD vectors [32 i, 32 i + 32); thread (warp w, lane l) owns vector
+// l of its NVT tiles.  Row j only touches the vectors >= j / EPV, so a tile's work grows with its index.  Two deals:
+// plain (warp w owns tiles w, 4 + w, 8 + w, ...) and serpentine (w, 7 - w, 8 + w, 15 - w, ...: every warp, i.e. every
+// SM sub-partition, gets the same share of the triangle).  The sweep is bound by the latency of the panel hand-offs,
+// not by issue slots, and the plain deal measures slightly faster; the serpentine one is kept as a build switch.
 #ifndef VB_FAST_BALANCE
-#define VB_FAST_BALANCE 1
+#define VB_FAST_BALANCE 0       // measured on B200 (C2 workload): 1.017 ms plain vs 1.038 ms serpentine
 #endif
 __device__ __forceinline__ int fast_tile(int w, int c) {
 #if VB_FAST_BALANCE
@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     constexpr int EPV = LdTraits<U>::EPV;
     constexpr int NVT = 32 / EPV;                        // LD vectors per thread per row
     constexpr bool DP4A = std::is_same<U, int8_t>::value;
+    // per-panel tile classification pays with two tiles per thread (int8); with four or eight (int16, float LD) the
+    // flag arrays cost more registers and branches than they save (measured: C4 sweep 1.69 -> 1.94 ms), so those
+    // types keep the general predicated form for every tile
+    constexpr bool CLASSIFY = (NVT <= 2);
     extern __shared__ __align__(128) unsigned char smem[];
 
     SmemView<T> sm;
@@ -236,8 +240,12 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
                 const int tb = 32 * fast_tile(wa, c);
-                live[c] = (tb + 32 > vmin) && (tb < vmax);
-                inter[c] = quad && (tb >= lo_all) && (tb + 32 <= hi_all);
+                if constexpr (CLASSIFY) {
+                    live[c] = (tb + 32 > vmin) && (tb < vmax);
+                    inter[c] = quad && (tb >= lo_all) && (tb + 32 <= hi_all);
+                } else {
+                    live[c] = true; inter[c] = false;        // general form only (see CLASSIFY)
+                }
                 anyl |= live[c];
                 anyb |= live[c] && !inter[c];
             }
@@ -387,8 +395,12 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
 #pragma unroll
             for (int c = 0; c < NVT; ++c) {
                 const int tb = 32 * fast_tile(wc, c);
-                live[c] = (tb + 32 > max(vmin, cut0)) && (tb < vmax);
-                inter[c] = quad && (tb >= lo_c) && (tb + 32 <= hi_c);
+                if constexpr (CLASSIFY) {
+                    live[c] = (tb + 32 > max(vmin, cut0)) && (tb < vmax);
+                    inter[c] = quad && (tb >= lo_c) && (tb + 32 <= hi_c);
+                } else {
+                    live[c] = true; inter[c] = false;
+                }
                 anyl |= live[c];
                 anyb |= live[c] && !inter[c];
             }
