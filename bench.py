@@ -327,12 +327,12 @@ def main():
     kname = {"viprs": "vb::sweep_fast_kernel<int8,SlabModel>", "mix": "vb::sweep_fast_kernel<int16,MixModel<4>>",
              "grid": "vb::grid_sweep_kernel<float,int8>"}[wl["model"]]
     # dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the ncu passes committed under profiles/
-    traffic = {"c2": 2.344e9, "c3": 16.82e9, "c4": 4.667e9}.get(args.workload)
+    traffic = {"c2": 2.337e9, "c3": 16.82e9, "c4": 4.668e9}.get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kname, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "traffic_source": {"c2": "profiles/r01_c2_launches_l2ahead0.csv", "c3": "profiles/r01_c3_launches_dram.csv",
-                                   "c4": "profiles/r01_c4_launches_dram.csv"}.get(args.workload)}
+                "traffic_source": {"c2": "profiles/r01b_c2_launches.csv", "c3": "profiles/r01_c3_launches_dram.csv",
+                                   "c4": "profiles/r01b_c4_launches.csv"}.get(args.workload)}
     if wl["model"] == "grid":
         fma = 2.0 * nnz * G
         roofline["fp32_pipe_frac"] = fma / (kern_ms * 1e-3) / FP32_FMA_PER_S
