@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+( time timeout 900 python -m pytest tests/test_full_size_gpu.py -m gpu -x -q ) 2>&1 | tail -15
