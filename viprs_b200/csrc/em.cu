@@ -17,6 +17,39 @@ constexpr int EM_THREADS = 256;
 
 struct Theta { double sigma_epsilon, tau_beta, pi, lambda_min; };
 
+// float32 state: the per-element transcendental work of the two streaming kernels is what bounds them at G = 256
+// (profiles/r01b_c3_launches.csv), so where the INPUT is an exact float32 number the logarithm is taken in float32
+// (<= 1 ulp of the result, i.e. as accurate as the float32 input deserves; accumulation stays float64), and double
+// reciprocals start from the float32 reciprocal plus one Newton step (relative error ~4e-15).  float64 state: IEEE.
+template <typename T> __device__ __forceinline__ double rcp_em(double d) {
+    if constexpr (sizeof(T) == 4) {
+        const double r = (double)__frcp_rn((float)d);
+        return r * (2.0 - d * r);
+    } else {
+        return 1.0 / d;
+    }
+}
+// log(x) for x = clip(g), g an exact value of type T in [0, 1]
+template <typename T> __device__ __forceinline__ double log_unit(double xc) {
+    if constexpr (sizeof(T) == 4) return (double)logf((float)xc);
+    else return log(xc);
+}
+// log(clip(1 - p)) for an exact p of type T in [0, 1]: 1 - p is ill-conditioned near 1, log1p is not
+template <typename T> __device__ __forceinline__ double log_one_minus(double p, double ngc) {
+    if constexpr (sizeof(T) == 4) {
+        const double res = 1e-15;
+        if (ngc <= res || ngc >= 1.0 - res) return log(ngc);                  // clipped: rare, exact
+        return p <= 0.5 ? (double)log1pf(-(float)p) : (double)logf((float)(1.0 - p));   // 1 - p is exact for p >= 0.5
+    } else {
+        return log(ngc);
+    }
+}
+
+__device__ __forceinline__ double clip_res(double g) {                              // VIPRS.py:509-518
+    const double res = 1e-15;                                                       // np.finfo(np.float64).resolution
+    return fmin(fmax(g, res), 1.0 - res);
+}
+
 // layout 0: (M, ncol) column-major (single model: ncol = 1; grid), 1: (M, ncol) row-major (mixture, ncol = K)
 template <typename T>
 __global__ void __launch_bounds__(EM_THREADS) prepare_kernel(int M, int ncol, int layout, int half_tau,
@@ -38,7 +71,7 @@ __global__ void __launch_bounds__(EM_THREADS) prepare_kernel(int M, int ncol, in
         const double n = n_per_snp[j];
         const double vt = n * nscale + th.tau_beta;
         const size_t e = layout == 0 ? (size_t)c * M + j : (size_t)j * ncol + c;
-        mu_mult[e] = (T)(n / (vt * th.sigma_epsilon));                              // VIPRS.py:404
+        mu_mult[e] = (T)(n * rcp_em<T>(vt * th.sigma_epsilon));                              // VIPRS.py:404
         u_logs[e] = (T)(cst - 0.5 * log(vt));                                       // VIPRS.py:405-406
         tau_term[e] = (T)(half_tau ? 0.5 * vt : sqrt(0.5 * vt));                    // e_step.hpp:616 / VIPRS.py:418
         if (log_null_pi != nullptr && c == 0) log_null_pi[j] = (T)lnp;
@@ -46,11 +79,6 @@ __global__ void __launch_bounds__(EM_THREADS) prepare_kernel(int M, int ncol, in
 }
 
 constexpr int NS = VIPRS_B200_NSUMS;
-
-__device__ __forceinline__ double clip_res(double g) {                              // VIPRS.py:509-518
-    const double res = 1e-15;                                                       // np.finfo(np.float64).resolution
-    return fmin(fmax(g, res), 1.0 - res);
-}
 
 // grid = (chunks, nseg, ncol).  partial[((seg * ncol + c) * chunks + chunk) * NS + slot]; the last CTA of every
 // (seg, c) adds the chunk partials in chunk order and writes sums[(seg * ncol + c) * NS + slot].
@@ -83,9 +111,9 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
         const double gc = clip_res(g);
         acc[VIPRS_B200_S_GAMMA] += g;                                               // VIPRS.py:434
         acc[VIPRS_B200_S_GAMMA_MU2] += g * mu * mu;                                 // zeta, VIPRS.py:896
-        const double ivt = 1.0 / vt;
+        const double ivt = rcp_em<T>(vt);
         acc[VIPRS_B200_S_G_INV_TAU] += g * ivt;
-        acc[VIPRS_B200_S_G_LOGG] += gc * log(gc);                                   // VIPRS.py:562
+        acc[VIPRS_B200_S_G_LOGG] += gc * log_unit<T>(gc);                                   // VIPRS.py:562
         acc[VIPRS_B200_S_GCLIP] += gc;
         acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(same_tau ? vt : n * nscale_l + tl.tau_beta);   // VIPRS.py:565 (log_var_tau cache)
         acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);                          // VIPRS.py:571-573
@@ -103,7 +131,7 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
             const double ng = clip_res(1.0 - pip);
             acc[VIPRS_B200_S_ETA_Q] += q_scale * et * (double)q[ev];                // VIPRS.py:455
             acc[VIPRS_B200_S_BETA_ETA] += (double)std_beta[j] * et;                 // VIPRS.py:469
-            acc[VIPRS_B200_S_NG_LOGNG] += ng * log(ng);                             // VIPRS.py:563
+            acc[VIPRS_B200_S_NG_LOGNG] += ng * log_one_minus<T>(pip, ng);                             // VIPRS.py:563
             acc[VIPRS_B200_S_NGCLIP] += ng;
             acc[VIPRS_B200_S_ETA2] += et * et;                                      // VIPRS.py:703
             acc[VIPRS_B200_S_MAX_DIFF] = fmax(acc[VIPRS_B200_S_MAX_DIFF], fabs((double)eta_diff[ev]));   // VIPRS.py:997
