@@ -60,6 +60,10 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
 // plain (warp w owns tiles w, 4 + w, 8 + w, ...) and serpentine (w, 7 - w, 8 + w, 15 - w, ...: every warp, i.e. every
 // SM sub-partition, gets the same share of the triangle).  The sweep is bound by the latency of the panel hand-offs,
 // not by issue slots, and the plain deal measures slightly faster; the serpentine one is kept as a build switch.
+#ifndef VB_GROUP_UNROLL
+#define VB_GROUP_UNROLL 1          // unroll factor of the A / C row-group loops (2: 1.02 -> 1.25 ms on C2: spills, instruction cache)
+#endif
+constexpr int kGroupUnroll = VB_GROUP_UNROLL;
 #ifndef VB_FAST_BALANCE
 #define VB_FAST_BALANCE 0       // measured on B200 (C2 workload): 1.017 ms plain vs 1.038 ms serpentine
 #endif
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
                     if (lane < P) sm.partial[wa * RR + ((jl0 + lane) & (RR - 1))] = 0.f;
                 }
             } else {
-#pragma unroll 1
+#pragma unroll kGroupUnroll
                 for (int rg = 0; rg < P; rg += 4) {
                     const int nv = min(4, P - rg);
                     int mx[4];
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
                 anyb |= live[c] && !inter[c];
             }
             if (anyl) {
-#pragma unroll 1
+#pragma unroll kGroupUnroll
                 for (int rg = 0; rg < Pc; rg += 4) {
                     const int nv = min(4, Pc - rg);
                     int mx[4];
