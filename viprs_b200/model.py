@@ -229,8 +229,10 @@ class VIPRS:
         L = _lib.lib()
         wsb = int(L.viprs_b200_sums_workspace_bytes(max(M, 1), nc, nseg))
         self._ws = torch.zeros(max(wsb, 8), dtype=torch.uint8, device=dev)
-        self._sums_dev = torch.zeros((nseg, nc, _lib.NSUMS), dtype=torch.float64, device=dev)
         self._exchange = SumsExchange(nseg, nc, _lib.NSUMS, em_host.S_MAX_DIFF, self.rank, self.world, dev, self.group)
+        # world > 1: the sums kernel writes straight into the collective's send buffer
+        self._sums_dev = (self._exchange.table() if self.world > 1 else
+                          torch.zeros((nseg, nc, _lib.NSUMS), dtype=torch.float64, device=dev))
         self._q_is_forward = False
 
     def initialize_variational_parameters(self, param_0=None):

@@ -110,21 +110,34 @@ class SumsExchange:
         self.rank, self.world, self.group = rank, world, group
         self.n_main = nseg * ncol * nsums
         self.n_max = world * nseg * ncol
-        self.buf = torch.zeros(self.n_main + self.n_max, dtype=torch.float64, device=device)
+        # send: [this rank's table | one-hot maxima] -- the rows of the other ranks stay zero for ever, so nothing is
+        # cleared per iteration; recv: the copy the (in-place) collective works on, read back with ONE transfer
+        self.send = torch.zeros(self.n_main + self.n_max, dtype=torch.float64, device=device)
+        self.recv = torch.zeros_like(self.send)
+        self.host = torch.zeros_like(self.send, device="cpu")
+        if torch.device(device).type == "cuda":
+            self.host = self.host.pin_memory()
+
+    def table(self):
+        """(nseg, ncol, nsums) view of the send buffer: let the sums kernel write here and all_reduce() copies nothing."""
+        return self.send[:self.n_main].view(self.nseg, self.ncol, self.nsums)
 
     def all_reduce(self, sums):
         """sums: (nseg, ncol, nsums) float64 tensor (device of the exchange) -> reduced numpy array."""
-        torch = self.torch
         if self.world == 1:
             return sums.detach().cpu().numpy().reshape(self.nseg, self.ncol, self.nsums).copy()
         import torch.distributed as dist
-        main = self.buf[:self.n_main].view(self.nseg, self.ncol, self.nsums)
-        main.copy_(sums.view(self.nseg, self.ncol, self.nsums))
-        mx = self.buf[self.n_main:].view(self.world, self.nseg, self.ncol)
-        mx.zero_()
-        mx[self.rank].copy_(main[:, :, self.max_slot])
-        main[:, :, self.max_slot] = 0.0
-        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
-        out = main.detach().cpu().numpy().copy()
-        out[:, :, self.max_slot] = mx.detach().cpu().numpy().max(axis=0)
+        main = self.table()
+        if sums.data_ptr() != main.data_ptr():
+            main.copy_(sums.view(self.nseg, self.ncol, self.nsums))
+        self.send[self.n_main:].view(self.world, self.nseg, self.ncol)[self.rank].copy_(main[:, :, self.max_slot])
+        self.recv.copy_(self.send)
+        dist.all_reduce(self.recv, op=dist.ReduceOp.SUM, group=self.group)
+        self.host.copy_(self.recv)                                   # synchronises (pageable or pinned destination)
+        if self.recv.is_cuda:
+            self.torch.cuda.current_stream().synchronize()
+        h = self.host.numpy()
+        out = h[:self.n_main].reshape(self.nseg, self.ncol, self.nsums).copy()
+        # the summed MAX_DIFF slot of the main table is meaningless: take the maximum over the one-hot rows
+        out[:, :, self.max_slot] = h[self.n_main:].reshape(self.world, self.nseg, self.ncol).max(axis=0)
         return out
