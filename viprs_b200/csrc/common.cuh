@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+#ifndef VB_TRYWAIT_NS
+#define VB_TRYWAIT_NS 20000     // suspend-time hint of mbarrier.try_wait (ns)
+#endif
 // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so the
 // waiting warps do not burn issue slots next to the working ones.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -47,7 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VB_TRYWAIT_NS)
         : "memory");
     return ok != 0;
 }

@@ -2,14 +2,17 @@
 //
 // Same algorithm, hand-offs, producer and chain warp as sweep.cuh; what changes is where the block state
 // lives and how the bulk work is split:
-//   warps 0..3  "A" : backward dots B_j = sum_{k>j} R_jk eta_k(old).  Thread t owns the LD vectors
-//                     v = t + 128 c (c < NVT = 32/EPV) of every row and keeps eta_old of its 32 columns in
+//   warps 0..3  "A" : backward dots B_j = sum_{k>j} R_jk eta_k(old).  Thread (warp w, lane l) owns vector l of its NVT =
+//                     32/EPV tiles of 32 LD vectors (fast_tile) of every row and keeps eta_old of its 32 columns in
 //                     REGISTERS.  int8 LD: eta_old is held as NLIMB balanced base-128 digits (int8) of a
 //                     block-scaled fixed-point value and the dot is IDP.4A (dp4a, u8 x s8 -> exact int32)
 //                     on the raw biased bytes -- no dequantisation instruction at all on this side.
 //   warps 4..7  "C" : forward axpy f_k += R_jk eta_j(new) with the same vector ownership and f in REGISTERS;
 //                     columns whose accumulation is complete are published to a 128-entry ring for the chain.
-// No eta / f arrays in shared memory => the whole 113 KB (two CTAs per SM) minus ~20 KB goes to the TMA ring.
+//                     Both classify their tiles per panel (dead / interior / boundary, see the A role below).
+// No eta / f arrays in shared memory => the whole 113 KB (two CTAs per SM) minus ~18 KB goes to the TMA ring.
+// What bounds this kernel (measured): the latency of one panel through TMA -> A -> chain -> C with
+// three stages in flight, not HBM and not issue slots.
 #pragma once
 #include <type_traits>
 
@@ -25,7 +28,6 @@ constexpr int FAST_WARPS = 10;
 constexpr int FAST_CHAIN_WARP = 9, FAST_PRODUCER_WARP = 8;
 __device__ __forceinline__ int fast_a_index(int warp) { return warp < 4 ? warp : -1; }
 __device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && warp < 8) ? warp - 4 : -1; }
-constexpr int GT = 128;                   // threads per bulk group
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
 constexpr int HP = 258;                   // entries of the fixed-point prefix sum (>= 4096/16 + 1; HP * 8 a multiple of 16)
