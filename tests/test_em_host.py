@@ -153,7 +153,11 @@ def _worker(rank, world, port, name, q):
                             (nn / (vt * th[0, 0])).astype(T), 1.0, 1, True)
                 S[i] = ocpu.sums_numpy(s["var_gamma"], s["var_mu"], s["eta"], s["q"], s["eta_diff"], L["std_beta"].astype(T),
                                        nn, th)
-            G = ex.all_reduce(torch.from_numpy(S))
+            if it % 2 == 0:
+                G = ex.all_reduce(torch.from_numpy(S))
+            else:                                   # the aliased path the device model uses: write into the send buffer
+                ex.table().copy_(torch.from_numpy(S))
+                G = ex.all_reduce(ex.table())
             em_host.slab_m_step(G, [shapes[c] for c in keys], n_snps, hyp, False, False, False)
             hist.append((float(em_host.slab_elbo(G, n_max, hyp, False)[0]), hyp.pi[0], hyp.tau_beta[0], hyp.sigma_epsilon[0],
                          float(em_host.max_eta_diff(G)[0])))
