@@ -125,7 +125,11 @@ class SumsExchange:
     def all_reduce(self, sums):
         """sums: (nseg, ncol, nsums) float64 tensor (device of the exchange) -> reduced numpy array."""
         if self.world == 1:
-            return sums.detach().cpu().numpy().reshape(self.nseg, self.ncol, self.nsums).copy()
+            if not sums.is_cuda:
+                return sums.detach().numpy().reshape(self.nseg, self.ncol, self.nsums).copy()
+            h = self.host[:self.n_main]
+            h.copy_(sums.reshape(-1))                                  # blocking read-back into pinned memory
+            return h.numpy().reshape(self.nseg, self.ncol, self.nsums).copy()
         import torch.distributed as dist
         main = self.table()
         if sums.data_ptr() != main.data_ptr():
