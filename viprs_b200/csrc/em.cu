@@ -29,6 +29,24 @@ template <typename T> __device__ __forceinline__ double rcp_em(double d) {
         return 1.0 / d;
     }
 }
+// log(var_tau) for a stream of nearby values (var_tau = n_j * nscale + tau_beta along one column).  float32 state:
+// one float64 logarithm per thread for its first value v0, then log(v) = log(v0) + log1p((v - v0) / v0) with the
+// log1p in float32 -- absolute error ~1e-8 on a value of ~13, i.e. two orders below float32 rounding of u_logs and
+// (used by the prepare kernel; in the sums kernel the extra state cost more than the logarithm it saved).
+// float64 state: the IEEE logarithm every time.
+template <typename T>
+struct LogNear {
+    double v0 = 0.0, l0 = 0.0, r0 = 0.0;
+    bool have = false;
+    __device__ __forceinline__ double operator()(double v) {
+        if constexpr (sizeof(T) == 4) {
+            if (!have) { v0 = v; l0 = log(v); r0 = 1.0 / v; have = true; return l0; }
+            return l0 + (double)log1pf((float)((v - v0) * r0));
+        } else {
+            return log(v);
+        }
+    }
+};
 // log(x) for x = clip(g), g an exact value of type T in [0, 1]
 template <typename T> __device__ __forceinline__ double log_unit(double xc) {
     if constexpr (sizeof(T) == 4) return (double)logf((float)xc);
@@ -67,12 +85,13 @@ __global__ void __launch_bounds__(EM_THREADS) prepare_kernel(int M, int ncol, in
         for (int k = 0; k < ncol; ++k) s += theta[k].pi;
         lnp = log(1.0 - s);
     }
+    LogNear<T> lognear;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
         const double n = n_per_snp[j];
         const double vt = n * nscale + th.tau_beta;
         const size_t e = layout == 0 ? (size_t)c * M + j : (size_t)j * ncol + c;
         mu_mult[e] = (T)(n * rcp_em<T>(vt * th.sigma_epsilon));                              // VIPRS.py:404
-        u_logs[e] = (T)(cst - 0.5 * log(vt));                                       // VIPRS.py:405-406
+        u_logs[e] = (T)(cst - 0.5 * lognear(vt));                                   // VIPRS.py:405-406
         tau_term[e] = (T)(half_tau ? 0.5 * vt : sqrt(0.5 * vt));                    // e_step.hpp:616 / VIPRS.py:418
         if (log_null_pi != nullptr && c == 0) log_null_pi[j] = (T)lnp;
     }
@@ -204,8 +223,12 @@ static int prepare_dispatch(int M, int ncol, int layout, int half_tau, const dou
                             T* tau_term, T* mu_mult, T* log_null_pi, cudaStream_t st) {
     if (M <= 0 || ncol <= 0 || !n || !theta || !u_logs || !tau_term || !mu_mult) return VIPRS_B200_EINVAL;
     if (layout != 0 && layout != 1) return VIPRS_B200_EINVAL;
-    int bx = (M + EM_THREADS - 1) / EM_THREADS;
+    // many columns (grid): ~8 rows per thread amortise LogNear's first logarithm; few columns: one row per thread,
+    // the launch is latency-sized and wants every SM busy
+    const int rpt = ncol >= 8 ? 8 : 1;
+    int bx = (M + rpt * EM_THREADS - 1) / (rpt * EM_THREADS);
     if (bx > 1184) bx = 1184;                       // 8 x 148: grid-stride beyond that
+    if (bx < 1) bx = 1;
     dim3 grid(bx, ncol);
     prepare_kernel<T><<<grid, EM_THREADS, 0, st>>>(M, ncol, layout, half_tau, n, reinterpret_cast<const Theta*>(theta),
                                                    u_logs, tau_term, mu_mult, log_null_pi);
