@@ -23,9 +23,12 @@ namespace vb {
 constexpr int NAW = 4;                    // A warps
 constexpr int NCW = 4;                    // C warps
 constexpr int NWW = 0;                    // progress-only warps between the A and C counters (none)
-// 10 warps per CTA: 0-3 A, 4-7 C, 8 producer, 9 chain (highest warp id).
+// 10 warps per CTA: 0-3 A, 4-7 C, 8 chain, 9 producer (see VB_CHAIN_WARP).
 constexpr int FAST_WARPS = 10;
-constexpr int FAST_CHAIN_WARP = 9, FAST_PRODUCER_WARP = 8;
+#ifndef VB_CHAIN_WARP
+#define VB_CHAIN_WARP 8         // 8: the chain shares its sub-partition with A0 / C0 (the lightest bulk warps), 9: with A1 / C1 (measured: C2 1.006 vs 1.020 ms, C4 1.702 vs 1.734 ms)
+#endif
+constexpr int FAST_CHAIN_WARP = VB_CHAIN_WARP, FAST_PRODUCER_WARP = 17 - VB_CHAIN_WARP;
 __device__ __forceinline__ int fast_a_index(int warp) { return warp < 4 ? warp : -1; }
 __device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && warp < 8) ? warp - 4 : -1; }
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
