@@ -70,10 +70,14 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
 #endif
 constexpr int kGroupUnroll = VB_GROUP_UNROLL;
 #ifndef VB_FAST_BALANCE
-#define VB_FAST_BALANCE 0       // measured on B200 (C2 workload): 1.017 ms plain vs 1.038 ms serpentine
+#define VB_FAST_BALANCE 0       // measured on B200 (C2 workload): plain 1.007 ms, serpentine (1) 1.038 ms, load-aware (2) 1.014 ms
 #endif
 __device__ __forceinline__ int fast_tile(int w, int c) {
-#if VB_FAST_BALANCE
+#if VB_FAST_BALANCE == 2
+    // warp 0 keeps the plain (lightest) pair because its sub-partition also hosts the chain warp; warps 1..3 are
+    // dealt the odd rounds in reverse: tiles {0,4}, {1,7}, {2,6}, {3,5} -> loads 5 : 9 : 9 : 9 (+ chain, + producer)
+    return 4 * c + (((c & 1) && w > 0) ? 4 - w : w);
+#elif VB_FAST_BALANCE
     return 4 * c + ((c & 1) ? 3 - w : w);
 #else
     return 4 * c + w;
