@@ -42,9 +42,9 @@ extern "C" {
 #define VIPRS_B200_OK               0
 #define VIPRS_B200_EINVAL          -1   /* bad argument (null pointer, bad dtype, M <= 0 ...)        */
 #define VIPRS_B200_ELAYOUT         -2   /* LD arrays inconsistent (run leaves [0,M), negative length) */
-#define VIPRS_B200_EBLOCK_TOO_LARGE -3  /* an LD block (connected run of overlapping rows) does not
-                                           fit the per-CTA shared-memory state; non-block (windowed /
-                                           banded genome-wide) LD lands here                          */
+#define VIPRS_B200_EBLOCK_TOO_LARGE -3  /* grid sweep only: an LD block (connected run of overlapping
+                                           rows) is larger than 4096 SNPs.  The single-model and mixture
+                                           sweeps tile larger blocks (and banded / windowed LD)       */
 #define VIPRS_B200_ENOMEM          -4
 #define VIPRS_B200_ENODEVICE       -5   /* no CUDA device: there is NO CPU fallback                  */
 #define VIPRS_B200_EUNSUPPORTED    -6   /* (T,U) combination or K not built                          */
@@ -71,6 +71,11 @@ typedef struct {
     int64_t smem_bytes;      /* dynamic shared memory per CTA the float32 sweep will request  */
     int32_t ring_stages;     /* depth of the TMA ring (float32 state)                         */
     int32_t ctas_per_sm;     /* CTAs (LD blocks) that share one SM (float32 state)            */
+    int32_t n_units;         /* sweep units: n_blocks, plus the extra tiles of LD blocks larger
+                                than 4096 rows (tiled sweep, see viprs_b200_e_step_*)         */
+    int32_t n_phases;        /* sweep launches per E-step: 1, or the tile count of the largest
+                                LD block                                                      */
+    int64_t ext_elems;       /* elements stored in the between-tile rectangles (0 if untiled) */
 } viprs_b200_ld_info_t;
 
 /* Replaces the reference's LD load (VIPRS.py:153-172: ld_mat.load(...) -> ld_data/ld_indptr/
@@ -93,11 +98,18 @@ int viprs_b200_ld_destroy(viprs_b200_ld_t* ld);
  * sweep is always the strictly sequential order and the LD is always upper-triangular on device.
  *
  * q handling: the sweep reads the LD once.  It leaves in `q` the forward part
- * dq_scale * sum_{i<j} R_ij eta_i(new).  If materialize_q != 0 a second streaming pass adds the
- * backward part so that `q` equals the reference's q after its second pass
- * (update_q_factor, e_step.hpp:307-338).  On entry `q` is ignored: the backward part is recomputed
- * from `eta`, which must therefore be consistent with (var_gamma, var_mu) as it is in the reference
- * (VIPRS.py:355-358).
+ * dq_scale * sum_{i<j} R_ij eta_i(new) (+ q_offset).  If materialize_q != 0 a second streaming pass adds
+ * the backward part so that `q` equals the reference's q after its second pass
+ * (update_q_factor, e_step.hpp:307-338).  The array `q` itself is not read on entry: the sweep recomputes
+ * dq (R - I) eta from `eta`.  The reference instead maintains q incrementally (e_step.hpp:421,439), so
+ * whatever its q holds beyond dq (R - I) eta on entry stays there for ever -- e.g. q = 0 next to eta != 0
+ * after a `param_0` warm start (VIPRS.py:339-357).  To reproduce that, compute that constant part ONCE with
+ * viprs_b200_q_offset_*(ld, eta_in, q_in, dq, out) and pass it as `q_offset` (device array, M entries, q
+ * units; NULL = none) to every sweep.  The host drop-ins viprs_b200_cpp_e_step* always do this.
+ *
+ * LD blocks larger than 4096 SNPs (e.g. 10,240-SNP float64 blocks, or banded / windowed LD where a whole
+ * chromosome is one block) are swept in 2048-row tiles: same per-SNP order, one launch per tile index plus
+ * streaming products over the rectangles between tiles (viprs_b200_ld_info_t.n_phases launches).
  *
  * The reductions the M-step / ELBO need are produced by viprs_b200_sums_* (VIPRS_B200_S_* slots below).
  */
@@ -119,12 +131,17 @@ int viprs_b200_ld_destroy(viprs_b200_ld_t* ld);
 int viprs_b200_e_step_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
                           float* var_mu, float* eta, float* q, float* eta_diff,
                           const float* u_logs, const float* sqrt_half_var_tau, const float* mu_mult,
-                          float dq_scale, int32_t materialize_q, void* stream);
+                          float dq_scale, int32_t materialize_q, const float* q_offset, void* stream);
 int viprs_b200_e_step_f64(const viprs_b200_ld_t* ld, const double* std_beta, double* var_gamma,
                           double* var_mu, double* eta, double* q, double* eta_diff,
                           const double* u_logs, const double* sqrt_half_var_tau,
                           const double* mu_mult, double dq_scale, int32_t materialize_q,
-                          void* stream);
+                          const double* q_offset, void* stream);
+/* q_offset_out[j] = q[j] - dq_scale * sum_{k != j} R_jk eta[k]   (two streaming passes over the LD) */
+int viprs_b200_q_offset_f32(const viprs_b200_ld_t* ld, const float* eta, const float* q, float dq_scale,
+                            float* q_offset_out, void* stream);
+int viprs_b200_q_offset_f64(const viprs_b200_ld_t* ld, const double* eta, const double* q, double dq_scale,
+                            double* q_offset_out, void* stream);
 
 /* viprs_b200_e_step_mixture_{f32,f64}: one sweep with the semantics of e_step_mixture<T,U,I>(..., threads=1,
  * low_memory=true) (e_step.hpp:447-551); argument meaning and order of cpp_e_step_mixture
@@ -133,11 +150,12 @@ int viprs_b200_e_step_f64(const viprs_b200_ld_t* ld, const double* std_beta, dou
 int viprs_b200_e_step_mixture_f32(const viprs_b200_ld_t* ld, int32_t K, const float* std_beta, float* var_gamma,
                                   float* var_mu, float* eta, float* q, float* eta_diff, const float* log_null_pi,
                                   const float* u_logs, const float* sqrt_half_var_tau, const float* mu_mult,
-                                  float dq_scale, int32_t materialize_q, void* stream);
+                                  float dq_scale, int32_t materialize_q, const float* q_offset, void* stream);
 int viprs_b200_e_step_mixture_f64(const viprs_b200_ld_t* ld, int32_t K, const double* std_beta, double* var_gamma,
                                   double* var_mu, double* eta, double* q, double* eta_diff,
                                   const double* log_null_pi, const double* u_logs, const double* sqrt_half_var_tau,
-                                  const double* mu_mult, double dq_scale, int32_t materialize_q, void* stream);
+                                  const double* mu_mult, double dq_scale, int32_t materialize_q,
+                                  const double* q_offset, void* stream);
 
 /* viprs_b200_e_step_grid_{f32,f64}: one sweep with the semantics of e_step_grid<T,U,I>(..., threads=1)
  * followed by update_q_factor_matrix (e_step.hpp:555-647, 266-303); argument meaning of cpp_e_step_grid
@@ -165,8 +183,8 @@ int viprs_b200_backward_dot_f64(const viprs_b200_ld_t* ld, const double* x, doub
  * Same arrays, same in-place outputs as cpp_e_step(...) (e_step_cpp.pyx:91-122) with host (numpy)
  * buffers: upload, pack, sweep, materialise q, download.  `threads` is accepted and ignored
  * (the result is the threads=1 result); `low_memory` selects how the LD run is interpreted
- * (1: upper-triangular, 0: symmetric with diagonal).  On entry q must be consistent with eta
- * as in the reference; it is recomputed on the device. */
+ * (1: upper-triangular, 0: symmetric with diagonal).  q is in/out like the reference's: the part of
+ * the incoming q that eta does not explain is carried through the sweep (viprs_b200_q_offset_*). */
 int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, const void* ld_indptr,
                           int32_t indptr_is_i64, const void* ld_data, int32_t ld_dtype,
                           int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu,
@@ -181,6 +199,21 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
                                   void* eta, void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
                                   const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
                                   int32_t threads, int32_t low_memory);
+
+/* The same two calls for a caller that keeps the LD resident on the device (viprs_b200_ld_create once) but its state in
+ * host memory, as the reference does: per call the arrays cpp_e_step reads go host->device (std_beta, var_gamma, var_mu,
+ * eta, q, u_logs, sqrt_half_var_tau, mu_mult), one sweep runs, q is materialised, and what cpp_e_step writes
+ * (var_gamma, var_mu, eta, q, eta_diff) comes back; returns after the stream has drained.  Pinned host buffers make the
+ * copies asynchronous.  q_is_consistent != 0: the caller vouches that q = dq (R - I) eta on entry (true on every
+ * iteration of VIPRS.fit unless `param_0` was given) and the two extra LD passes of viprs_b200_q_offset_* are skipped. */
+int viprs_b200_cpp_e_step_resident(const viprs_b200_ld_t* ld, int32_t float_dtype, const void* std_beta, void* var_gamma,
+                                   void* var_mu, void* eta, void* q, void* eta_diff, const void* u_logs,
+                                   const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
+                                   int32_t q_is_consistent, void* stream);
+int viprs_b200_cpp_e_step_mixture_resident(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, const void* std_beta,
+                                           void* var_gamma, void* var_mu, void* eta, void* q, void* eta_diff,
+                                           const void* log_null_pi, const void* u_logs, const void* sqrt_half_var_tau,
+                                           const void* mu_mult, double dq_scale, int32_t q_is_consistent, void* stream);
 
 /* ---- the per-iteration work around the sweep ------------------------------------------------------------
  *

@@ -207,13 +207,20 @@ class OracleVIPRS:
         self.lambda_min = ft(self.lambda_min)
         self._sigma_g = ft(0.)
 
-    # VIPRS.py:318-359
-    def initialize_variational_parameters(self):
+    # VIPRS.py:318-359 (param_0 may carry 'mu' / 'gamma', :339-351; q starts at 0 either way, :357)
+    def initialize_variational_parameters(self, param_0=None):
+        param_0 = param_0 or {}
         self.var_mu, self.var_tau, self.var_gamma = {}, {}, {}
         for c, shp in self._param_shapes().items():
             self.var_tau[c] = (self._n(c) / self.sigma_epsilon) + self.tau_beta
-            self.var_mu[c] = np.zeros(shp, dtype=self.float_precision)
-            self.var_gamma[c] = self.pi * np.ones(shp, dtype=self.float_precision)
+            if "mu" in param_0:
+                self.var_mu[c] = np.array(param_0["mu"][c]).astype(self.float_precision)
+            else:
+                self.var_mu[c] = np.zeros(shp, dtype=self.float_precision)
+            if "gamma" in param_0:
+                self.var_gamma[c] = np.array(param_0["gamma"][c]).astype(self.float_precision)
+            else:
+                self.var_gamma[c] = self.pi * np.ones(shp, dtype=self.float_precision)
         self.eta = self.compute_eta()
         self.zeta = self.compute_zeta()
         self.eta_diff = {c: np.zeros_like(e, dtype=self.float_precision) for c, e in self.eta.items()}
@@ -226,9 +233,9 @@ class OracleVIPRS:
     def _n(self, c):
         return self.n_per_snp[c]
 
-    def initialize(self, theta_0=None):
+    def initialize(self, theta_0=None, param_0=None):
         self.initialize_theta(theta_0)
-        self.initialize_variational_parameters()
+        self.initialize_variational_parameters(param_0) if param_0 else self.initialize_variational_parameters()
         self.history = {"ELBO": [], "sigma_epsilon": [], "tau_beta": [], "pi": [], "sigma_g": [],
                         "max_eta_diff": [], "mse": []}
 
@@ -307,9 +314,9 @@ class OracleVIPRS:
     def get_heritability(self):                          # VIPRS.py:780-785
         return self._sigma_g / (self._sigma_g + self.sigma_epsilon)
 
-    def run(self, n_iter, theta_0=None):
+    def run(self, n_iter, theta_0=None, param_0=None):
         """The body of VIPRS.fit's main loop (VIPRS.py:979-1000) for a fixed iteration count."""
-        self.initialize(theta_0)
+        self.initialize(theta_0, param_0)
         for _ in range(n_iter):
             self.e_step()
             self.m_step()

@@ -195,3 +195,39 @@ def test_sharded_em_over_gloo_matches_single_process(oracle_built, world):
         segs = sorted(r[2][c] for r in res if r[2][c][1] > r[2][c][0])
         assert segs[0][0] == 0 and segs[-1][1] == len(ch[c]["std_beta"])
         assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+
+
+def test_fit_status_behaves_like_the_reference_optimize_result():
+    """viprs_b200.optim restates viprs/utils/OptimizeResult.py; where the reference is importable (this container, not
+    the GPU box) random update sequences must leave both in the same state."""
+    import importlib.util
+    import os
+    ref_path = "/root/reference/viprs/utils/OptimizeResult.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("_ref_optres", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from viprs_b200.optim import FitStatus, Streak
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        a, b = ref.OptimizeResult(), FitStatus()
+        a.reset(); b.reset()
+        ca, cb = ref.IterationConditionCounter(), Streak()
+        f, it = 0.0, 0
+        for step in range(40):
+            f += rng.choice([-1.0, 1.0, 0.0, 0.5])
+            stop = bool(rng.random() < 0.05)
+            succ = bool(stop and rng.random() < 0.5)
+            msg = rng.choice(["ok", "Maximum iterations reached", "diverged"])
+            inc = bool(rng.random() < 0.9)
+            a.update(f, stop_iteration=stop, success=succ, message=msg, increment=inc)
+            b.update(f, stop_iteration=stop, success=succ, message=msg, increment=inc)
+            it += int(rng.integers(1, 3))
+            cond = bool(rng.random() < 0.7)
+            ca.update(cond, it); cb.update(cond, it)
+            assert (a.fun, a.nit, a.stop_iteration, a.success, a.message, a.error_on_termination, a.oscillation_counter,
+                    bool(a.valid_optim_result)) == \
+                   (b.fun, b.nit, b.stop_iteration, b.success, b.message, b.error_on_termination, b.oscillation_counter,
+                    bool(b.valid_optim_result))
+            assert ca.counter == cb.counter

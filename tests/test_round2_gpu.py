@@ -1,0 +1,301 @@
+"""
+GPU parity tests added in round 2 (all through the C ABI, against the compiled reference / the oracle):
+
+  * tiled sweep: LD blocks larger than 4096 SNPs (float64 10,240-SNP blocks = BASELINE configs[4] shape, int8
+    9,000-SNP block) and banded LD where a whole "chromosome" is one block;
+  * q is in/out like the reference's: q_in that eta_in does not explain is carried through the sweeps
+    (`param_0` warm start: eta != 0 next to q = 0, VIPRS.py:339-357);
+  * BASELINE hyper-parameters (n = 3e5, h2 = 0.3, pi = 0.01, sigma_epsilon = 0.8) on one 4096-SNP C2 block (int8)
+    and one C4 block (int16, K = 4) after {10, 50} sweeps, against the float32 AND the float64 reference; the
+    measured numbers go to gpurun_out/parity_floor.json;
+  * 10-iteration EM history (ELBO, pi, sigma_epsilon, tau_beta) on a 16-block slice of the C2 workload.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, relmax
+from tests_util import make_block_ld
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import viprs_b200
+    return viprs_b200
+
+
+def _hyper(rng, M, T, pi=0.02, se=0.8):
+    n = np.floor(rng.uniform(4e4, 6e4, M))
+    tau = pi * M / (1 - se)
+    vt = n / se + tau
+    u_logs = (np.log(pi) - np.log(1 - pi) + .5 * (np.log(tau) - np.log(vt))).astype(T)
+    return u_logs, np.sqrt(.5 * vt).astype(T), (n / (vt * se)).astype(T), pi
+
+
+def _sweeps(fn, P, T, hy, n_sweeps, st=None):
+    M = P["M"]
+    u_logs, shvt, mm, pi = hy
+    if st is None:
+        st = {k: np.zeros(M, T) for k in ("var_mu", "eta", "q", "eta_diff")}
+        st["var_gamma"] = np.full(M, pi, T)
+    for _ in range(n_sweeps):
+        fn(P["lb"], P["indptr"], P["data"], P["beta"], st["var_gamma"], st["var_mu"], st["eta"], st["q"],
+           st["eta_diff"], u_logs, shvt, mm, P["dq"], 1, True)
+    return st
+
+
+def _record(name, payload):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "parity_floor.json")
+    d = {}
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            d = {}
+    d[name] = payload
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tiled sweep
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tn,un,blocks", [("f64", "f64", (5000, 300)), ("f32", "i8", (9000, 64, 4500)),
+                                          ("f64", "i16", (4097,)), ("f32", "f32", (6200,))])
+def test_tiled_blocks_match_oracle(vb, oracle_built, tn, un, blocks):
+    T = np.float32 if tn == "f32" else np.float64
+    U = {"i8": np.int8, "i16": np.int16, "f32": np.float32, "f64": np.float64}[un]
+    rng = np.random.default_rng(len(blocks) * 31 + blocks[0])
+    P = make_block_ld(rng, blocks, U, T)
+    hy = _hyper(rng, P["M"], T)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    assert ld.n_blocks == len(blocks) and ld.max_block == max(blocks)
+    assert ld.n_phases == -(-max(blocks) // 2048) and ld.n_units > ld.n_blocks and ld.ext_elems > 0
+    ld.destroy()
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
+    tol = 1e-4 if T == np.float32 else 1e-10
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= tol, (k, relmax(got[k], ref[k]))
+
+
+def test_c5_shape_block_float64(vb, oracle_built):
+    """BASELINE configs[4] shape: float64 state + float64 LD, one 10,240-SNP block (~5k stored entries per row)."""
+    T = np.float64
+    rng = np.random.default_rng(55)
+    P = make_block_ld(rng, (10240, 128), np.float64, T)
+    hy = _hyper(rng, P["M"], T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 2)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 2)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= 1e-10, (k, relmax(got[k], ref[k]))
+
+
+def _banded(rng, M, w, U, T):
+    """Windowed LD: row j stores columns j+1 .. min(j+w, M-1) -- no independent blocks at all."""
+    lens = np.minimum(w, M - 1 - np.arange(M)).astype(np.int64)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dist = np.concatenate([np.arange(1, k + 1) for k in lens])
+    vals = 0.35 * np.exp(-dist / (0.2 * w)) * np.cos(dist * 0.37) + 0.01 * rng.standard_normal(dist.shape[0])
+    if U == np.int8:
+        data, dq = np.rint(vals * 127).astype(np.int8), 1. / 127
+    else:
+        data, dq = vals.astype(U), 1.
+    beta = (rng.standard_normal(M) / np.sqrt(5e4) + 0.004 * (rng.random(M) < 0.02) * rng.standard_normal(M)).astype(T)
+    return {"M": M, "data": data, "indptr": indptr, "lb": np.arange(1, M + 1, dtype=np.int32), "beta": beta, "dq": dq}
+
+
+@pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f64", "f64")])
+def test_banded_ld_is_swept_in_order(vb, oracle_built, tn, un):
+    T = np.float32 if tn == "f32" else np.float64
+    U = np.int8 if un == "i8" else np.float64
+    rng = np.random.default_rng(77)
+    P = _banded(rng, 7001, 650, U, T)
+    hy = _hyper(rng, P["M"], T)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    assert ld.n_blocks == 1 and ld.n_phases == 4
+    ld.destroy()
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
+    tol = 1e-4 if T == np.float32 else 1e-10
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= tol, (k, relmax(got[k], ref[k]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# q is in/out
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tn,un,blocks", [("f32", "i8", (700, 33, 257)), ("f64", "f64", (300, 120)),
+                                          ("f64", "f64", (4500,))])
+@pytest.mark.parametrize("q_in", ["zero", "garbage"])
+def test_incoming_q_is_honoured(vb, oracle_built, tn, un, blocks, q_in):
+    """eta_in != 0 with q_in = 0 (a param_0 warm start, VIPRS.py:339-357) or an arbitrary q_in: the reference keeps
+    q incrementally, so the unexplained part of q_in stays; the drop-in must reproduce that."""
+    T = np.float32 if tn == "f32" else np.float64
+    U = np.int8 if un == "i8" else np.float64
+    rng = np.random.default_rng(5)
+    P = make_block_ld(rng, blocks, U, T)
+    M = P["M"]
+    hy = _hyper(rng, M, T)
+
+    def start():
+        st = {"var_gamma": rng0.uniform(0.01, 0.3, M).astype(T), "var_mu": (0.01 * rng0.standard_normal(M)).astype(T),
+              "eta_diff": np.zeros(M, T)}
+        st["eta"] = st["var_gamma"] * st["var_mu"]
+        st["q"] = np.zeros(M, T) if q_in == "zero" else (0.003 * rng0.standard_normal(M)).astype(T)
+        return st
+
+    rng0 = np.random.default_rng(9)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 2, start())
+    rng0 = np.random.default_rng(9)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 2, start())
+    tol = 1e-4 if T == np.float32 else 1e-10
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= tol, (k, relmax(got[k], ref[k]))
+
+
+def test_fit_with_param_0_matches_oracle(vb, oracle_built):
+    from oracle import cpu as ocpu
+    from viprs_b200.model import VIPRS
+    T = np.float32
+    rng = np.random.default_rng(21)
+    P = make_block_ld(rng, (300, 517, 64), np.int8, T)
+    M = P["M"]
+    n = np.full(M, 5e4)
+    param_0 = {"mu": {1: (0.004 * rng.standard_normal(M)).astype(T)}, "gamma": {1: rng.uniform(0.01, 0.2, M).astype(T)}}
+    theta_0 = {"pi": 0.02, "sigma_epsilon": 0.8}
+    o = ocpu.OracleVIPRS({1: (P["data"], P["indptr"], P["lb"])}, {1: P["beta"]}, {1: n}, float_precision="float32",
+                         dequantize_on_the_fly=True)
+    o.run(4, dict(theta_0), param_0)
+    m = VIPRS(data={1: dict(ld_data=P["data"], ld_indptr=P["indptr"], ld_left_bound=P["lb"], std_beta=P["beta"], n_per_snp=n)},
+              float_precision="float32")
+    m.fit(max_iter=4, min_iter=10, theta_0=dict(theta_0), param_0=param_0)
+    got = np.array(m.history["ELBO"][1:])
+    assert np.max(np.abs(got - np.array(o.history["ELBO"])) / np.abs(np.array(o.history["ELBO"]))) <= 1e-4
+    assert relmax(m.post_mean_beta[1], o.eta[1]) <= 1e-4
+    assert relmax(m.q[1].cpu().numpy(), o.q[1]) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE hyper-parameters past 2 sweeps
+# ---------------------------------------------------------------------------------------------------------
+def _baseline_block(ld_dtype, seed=7209):
+    import torch
+    from viprs_b200 import synth
+    inp = synth.make_inputs([4096], ld_dtype=ld_dtype, float_dtype=torch.float32, device="cpu", seed=seed)   # n = 3e5, h2 = 0.3
+    return inp
+
+
+@pytest.mark.parametrize("n_sweeps", [10, 50])
+def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
+    """int8 LD, one 4096-SNP block of the C2 workload, BASELINE's n / h2 / pi / sigma_epsilon, {10, 50} sweeps."""
+    from viprs_b200 import synth
+    inp = _baseline_block("int8")
+    M, pi, se = 4096, 0.01, 0.8
+    res = {}
+    for fdt, T in (("float32", np.float32), ("float64", np.float64)):
+        import torch
+        ul, sv, mm, _ = synth.e_step_inputs(inp["std_beta"], inp["n_per_snp"], pi, se, pi * 1101824 / (1 - se),
+                                            float_dtype=getattr(torch, fdt))
+        P = {"M": M, "lb": inp["ld_left_bound"].numpy(), "indptr": inp["ld_indptr"].numpy(), "data": inp["ld_data"].numpy(),
+             "beta": inp["std_beta"].numpy().astype(T), "dq": inp["dq_scale"]}
+        hy = (ul.numpy(), sv.numpy(), mm.numpy(), pi)
+        res["ref_" + fdt] = _sweeps(oracle_built.e_step, P, T, hy, n_sweeps)
+        if T == np.float32:
+            res["got3"] = _sweeps(vb.cpp_e_step, P, T, hy, n_sweeps)
+            os.environ["VIPRS_B200_LIMBS"] = "4"               # 28-bit fixed-point eta_old in the dp4a backward dots
+            try:
+                res["got4"] = _sweeps(vb.cpp_e_step, P, T, hy, n_sweeps)
+            finally:
+                del os.environ["VIPRS_B200_LIMBS"]
+    rec = {}
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        rec[k] = {"floor_ref32_vs_ref64": relmax(res["ref_float32"][k], res["ref_float64"][k]),
+                  "ours_vs_ref32": relmax(res["got3"][k], res["ref_float32"][k]),
+                  "ours_vs_ref64": relmax(res["got3"][k], res["ref_float64"][k]),
+                  "ours_limbs4_vs_ref64": relmax(res["got4"][k], res["ref_float64"][k]),
+                  "limbs3_vs_limbs4": relmax(res["got3"][k], res["got4"][k])}
+    _record(f"c2_block_int8_{n_sweeps}_sweeps", rec)
+    print(json.dumps(rec))
+    for k in ("eta", "var_gamma"):
+        r = rec[k]
+        # north star: within 1e-4 of the reference; where the float32 reference itself sits further than that from its
+        # float64 self, "the reference" is only defined to that floor: require to be as close to ref64 as ref32 is (x2)
+        assert r["ours_vs_ref32"] <= 1e-4 or r["ours_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
+        # the 21-bit fixed-point representation adds nothing visible next to float32 rounding
+        assert r["limbs3_vs_limbs4"] <= max(1e-4, 2 * r["floor_ref32_vs_ref64"]), (k, r)
+
+
+@pytest.mark.parametrize("n_sweeps", [10, 50])
+def test_c4_block_baseline_params(vb, oracle_built, n_sweeps):
+    """int16 LD, K = 4 mixture, one 4096-SNP block of the C4 workload, BASELINE parameters."""
+    inp = _baseline_block("int16")
+    M, K, se = 4096, 4, 0.8
+    d = 2.0 ** np.linspace(-3, 0, K)
+    pis = 0.01 * np.ones(K) / K
+    tau = d * (1101824 * np.dot(1. / d, pis) / (1 - se))
+    n = inp["n_per_snp"].numpy()
+    vt = n[:, None] / se + tau
+    res = {}
+    for T in (np.float32, np.float64):
+        C = lambda a: np.ascontiguousarray(a.astype(T))
+        ul, sv, mm = C(np.log(pis) - np.log1p(-pis) + .5 * (np.log(tau) - np.log(vt))), C(np.sqrt(.5 * vt)), C(n[:, None] / (vt * se))
+        lnp = np.full(M, np.log(1 - pis.sum()), T)
+        for name, fn in (("ref", oracle_built.e_step_mixture),) + ((("got", vb.cpp_e_step_mixture),) if T == np.float32 else ()):
+            st = {"var_gamma": C(np.tile(pis, (M, 1))), "var_mu": np.zeros((M, K), T), "eta": np.zeros(M, T),
+                  "q": np.zeros(M, T), "eta_diff": np.zeros(M, T)}
+            for _ in range(n_sweeps):
+                fn(inp["ld_left_bound"].numpy(), inp["ld_indptr"].numpy(), inp["ld_data"].numpy(),
+                   inp["std_beta"].numpy().astype(T), st["var_gamma"], st["var_mu"], st["eta"], st["q"], st["eta_diff"],
+                   lnp, ul, sv, mm, inp["dq_scale"], 1, True)
+            res[name + ("32" if T == np.float32 else "64")] = st
+    rec = {}
+    for k in ("eta", "var_gamma", "var_mu", "q"):
+        rec[k] = {"floor_ref32_vs_ref64": relmax(res["ref32"][k], res["ref64"][k]),
+                  "ours_vs_ref32": relmax(res["got32"][k], res["ref32"][k]),
+                  "ours_vs_ref64": relmax(res["got32"][k], res["ref64"][k])}
+    _record(f"c4_block_int16_K4_{n_sweeps}_sweeps", rec)
+    print(json.dumps(rec))
+    for k in ("eta", "var_gamma"):
+        r = rec[k]
+        assert r["ours_vs_ref32"] <= 1e-4 or r["ours_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# EM history at BASELINE block size
+# ---------------------------------------------------------------------------------------------------------
+def test_em_history_c2_slice(vb, oracle_built):
+    """10 EM iterations (E-step, M-step, ELBO) on a 16-block slice of the C2 workload (65,536 SNPs, int8 LD, n = 3e5):
+    ELBO / pi / sigma_epsilon / tau_beta per iteration against the numpy + compiled-reference restatement of VIPRS.fit."""
+    import torch
+    from oracle import cpu as ocpu
+    from viprs_b200 import synth
+    from viprs_b200.model import VIPRS
+    sizes = [4096] * 16
+    inp = synth.make_inputs(sizes, ld_dtype="int8", float_dtype=torch.float32, device="cpu")
+    theta_0 = {"pi": 0.01, "sigma_epsilon": 0.8}
+    lb, ip, ldd = inp["ld_left_bound"].numpy(), inp["ld_indptr"].numpy(), inp["ld_data"].numpy()
+    beta, n = inp["std_beta"].numpy(), inp["n_per_snp"].numpy()
+    o = ocpu.OracleVIPRS({1: (ldd, ip, lb)}, {1: beta}, {1: n}, float_precision="float32", dequantize_on_the_fly=True)
+    o.run(10, dict(theta_0))
+    m = VIPRS(data={1: dict(ld_data=inp["ld_data"], ld_indptr=inp["ld_indptr"], ld_left_bound=inp["ld_left_bound"],
+                            std_beta=inp["std_beta"], n_per_snp=inp["n_per_snp"])}, float_precision="float32",
+              tracked_params=["pi", "sigma_epsilon", "tau_beta"])
+    m.fit(max_iter=10, min_iter=20, theta_0=dict(theta_0), f_abs_tol=0., x_abs_tol=0.)
+    rec = {}
+    for key in ("ELBO", "pi", "sigma_epsilon", "tau_beta"):
+        a = np.array(m.history[key][1:], dtype=np.float64)[:10]          # entry 0 is the state before the first iteration
+        b = np.array(o.history[key], dtype=np.float64)
+        rec[key] = float(np.max(np.abs(a - b) / np.abs(b)))
+    _record("em_history_c2_16_blocks_10_iterations", rec)
+    print(json.dumps(rec))
+    for key, v in rec.items():
+        assert v <= 1e-4, (key, v)
+    assert relmax(m.post_mean_beta[1], o.eta[1]) <= 2e-4

@@ -9,7 +9,8 @@ hand-written CUDA kernels through a C ABI (include/viprs_b200.h) with ctypes.  N
 from ._lib import ViprsB200Error, lib, LIB_PATH  # noqa: F401
 from .ld import DeviceLD  # noqa: F401
 from .e_step import (cpp_e_step, cpp_e_step_mixture, cpp_e_step_grid, e_step_device,  # noqa: F401
-                     e_step_mixture_device, e_step_grid_device,
+                     e_step_mixture_device, e_step_grid_device, q_offset_device,
+                     cpp_e_step_resident, cpp_e_step_mixture_resident,
                      check_omp_support, check_blas_support)
 
 __version__ = "0.1.0"

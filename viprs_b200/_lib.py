@@ -25,7 +25,8 @@ class LdInfo(ctypes.Structure):
     _fields_ = [("M", ctypes.c_int32), ("ld_dtype", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
                 ("max_block", ctypes.c_int32), ("n_panels", ctypes.c_int32), ("stage_bytes", ctypes.c_int32),
                 ("nnz", ctypes.c_int64), ("packed_elems", ctypes.c_int64), ("smem_bytes", ctypes.c_int64),
-                ("ring_stages", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32)]
+                ("ring_stages", ctypes.c_int32), ("ctas_per_sm", ctypes.c_int32),
+                ("n_units", ctypes.c_int32), ("n_phases", ctypes.c_int32), ("ext_elems", ctypes.c_int64)]
 
 
 _lib = None
@@ -41,16 +42,20 @@ SIGNATURES = {
     "viprs_b200_ld_info": (ctypes.c_int, [_vp, ctypes.POINTER(LdInfo)]),
     "viprs_b200_ld_block_rows": (ctypes.c_int, [_vp, _vp]),
     "viprs_b200_ld_destroy": (ctypes.c_int, [_vp]),
-    "viprs_b200_e_step_f32": (ctypes.c_int, [_vp] * 10 + [_f32, _i32, _vp]),
-    "viprs_b200_e_step_f64": (ctypes.c_int, [_vp] * 10 + [_f64, _i32, _vp]),
-    "viprs_b200_e_step_mixture_f32": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f32, _i32, _vp]),
-    "viprs_b200_e_step_mixture_f64": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f64, _i32, _vp]),
+    "viprs_b200_e_step_f32": (ctypes.c_int, [_vp] * 10 + [_f32, _i32, _vp, _vp]),
+    "viprs_b200_e_step_f64": (ctypes.c_int, [_vp] * 10 + [_f64, _i32, _vp, _vp]),
+    "viprs_b200_q_offset_f32": (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp, _vp]),
+    "viprs_b200_q_offset_f64": (ctypes.c_int, [_vp, _vp, _vp, _f64, _vp, _vp]),
+    "viprs_b200_e_step_mixture_f32": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f32, _i32, _vp, _vp]),
+    "viprs_b200_e_step_mixture_f64": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f64, _i32, _vp, _vp]),
     "viprs_b200_e_step_grid_f32": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f32, _vp]),
     "viprs_b200_e_step_grid_f64": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f64, _vp]),
     "viprs_b200_backward_dot_f32": (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp]),
     "viprs_b200_backward_dot_f64": (ctypes.c_int, [_vp, _vp, _vp, _f64, _vp]),
     "viprs_b200_cpp_e_step": (ctypes.c_int, [_i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
     "viprs_b200_cpp_e_step_mixture": (ctypes.c_int, [_i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 10 + [_f64, _i32, _i32]),
+    "viprs_b200_cpp_e_step_resident": (ctypes.c_int, [_vp, _i32] + [_vp] * 9 + [_f64, _i32, _vp]),
+    "viprs_b200_cpp_e_step_mixture_resident": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f64, _i32, _vp]),
     "viprs_b200_prepare_f32": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 7),
     "viprs_b200_prepare_f64": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 7),
     "viprs_b200_sums_workspace_bytes": (_i64, [_i32, _i32, _i32]),

@@ -11,6 +11,8 @@ extern "C" int viprs_b200_ld_info(const viprs_b200_ld_t* h, viprs_b200_ld_info_t
     info->M = h->M; info->ld_dtype = h->ld_dtype; info->n_blocks = h->n_blocks; info->max_block = h->max_block;
     info->n_panels = h->n_panels; info->stage_bytes = h->stage_bytes; info->nnz = h->nnz;
     info->packed_elems = h->packed_elems;
+    info->n_blocks = h->n_ld_blocks; info->max_block = h->max_ld_block;
+    info->n_units = h->n_blocks; info->n_phases = h->n_phases; info->ext_elems = h->ext_elems;
     vb::RingGeometry g = vb::fast_ring_geometry(h);
     if (g.nst == 0) g = vb::ring_geometry(h, 4);
     info->smem_bytes = g.smem_bytes;
@@ -19,15 +21,85 @@ extern "C" int viprs_b200_ld_info(const viprs_b200_ld_t* h, viprs_b200_ld_info_t
     return VIPRS_B200_OK;
 }
 
-// ---- one-shot host-pointer drop-ins ------------------------------------------------------------------
+// ---- host-pointer drop-ins ------------------------------------------------------------------------------
 namespace {
 
-struct DevBuf {            // n arrays of nb bytes each, uploaded from host pointers
+struct DevBuf {            // scoped device allocation
     unsigned char* d = nullptr;
     ~DevBuf() { cudaFree(d); }
 };
 
-// K == 0: cpp_e_step; K > 0: cpp_e_step_mixture
+// One sweep with HOST state arrays on a device-resident LD matrix: upload what the reference's cpp_e_step* reads,
+// sweep, materialise q, download what it writes.  K == 0: cpp_e_step; K > 0: cpp_e_step_mixture.  The staging buffer
+// lives in the LD handle (grown on demand), so a per-iteration caller allocates nothing.
+int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, const void* std_beta, void* var_gamma,
+                    void* var_mu, void* eta, void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
+                    const void* shvt, const void* mu_mult, double dq_scale, int32_t q_is_consistent, cudaStream_t st) {
+    if (!ld) return VIPRS_B200_EINVAL;
+    if (float_dtype != VIPRS_B200_F32 && float_dtype != VIPRS_B200_F64) return VIPRS_B200_EINVAL;
+    if (!std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
+        return VIPRS_B200_EINVAL;
+    if (K > 0 && !log_null_pi) return VIPRS_B200_EINVAL;
+    const int32_t M = ld->M;
+    const size_t ts = float_dtype == VIPRS_B200_F32 ? 4 : 8;
+    const size_t kk = K > 0 ? (size_t)K : 1;
+    const size_t n1 = (((size_t)M * ts) + 255) & ~(size_t)255, nk = (((size_t)M * ts * kk) + 255) & ~(size_t)255;
+    const size_t c1 = (size_t)M * ts, ck = c1 * kk;
+    // layout: [beta][eta][q][diff][lnp][q offset] (n1 each) [gamma][mu][ulogs][shvt][mm] (nk each)
+    const size_t need = 6 * n1 + 5 * nk;
+    if (ld->host_ws_bytes < (int64_t)need) {
+        cudaFree(ld->d_host_ws);
+        ld->d_host_ws = nullptr; ld->host_ws_bytes = 0;
+        cudaError_t ea = cudaMalloc(&ld->d_host_ws, need);
+        if (ea != cudaSuccess) { cudaGetLastError(); return ea == cudaErrorMemoryAllocation ? VIPRS_B200_ENOMEM : (int)ea; }
+        ld->host_ws_bytes = (int64_t)need;
+    }
+    unsigned char* d = reinterpret_cast<unsigned char*>(ld->d_host_ws);
+    unsigned char *d_beta = d, *d_eta = d + n1, *d_q = d + 2 * n1, *d_diff = d + 3 * n1, *d_lnp = d + 4 * n1,
+                  *d_off = d + 5 * n1;
+    unsigned char *d_g = d + 6 * n1, *d_mu = d_g + nk, *d_ul = d_mu + nk, *d_sv = d_ul + nk, *d_mm = d_sv + nk;
+    cudaError_t e = cudaSuccess;
+    int rc = VIPRS_B200_OK;
+    auto up = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+    };
+    up(d_beta, std_beta, c1); up(d_eta, eta, c1); up(d_q, q, c1);
+    if (K > 0) up(d_lnp, log_null_pi, c1);
+    up(d_g, var_gamma, ck); up(d_mu, var_mu, ck); up(d_ul, u_logs, ck); up(d_sv, shvt, ck); up(d_mm, mu_mult, ck);
+    // q is in/out in the reference (maintained incrementally): unless the caller vouches that q_in = dq (R - I) eta_in
+    // (true on every iteration of VIPRS.fit without param_0), carry the part of q_in that eta_in does not explain
+    if (e == cudaSuccess) {
+        if (ts == 4) {
+            using F = float;
+            F* off = q_is_consistent ? nullptr : (F*)d_off;
+            if (off) rc = viprs_b200_q_offset_f32(ld, (F*)d_eta, (F*)d_q, (F)dq_scale, off, st);
+            if (rc == 0)
+                rc = K > 0 ? viprs_b200_e_step_mixture_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
+                                                           (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, off, st)
+                           : viprs_b200_e_step_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
+                                                   (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, off, st);
+        } else {
+            using F = double;
+            F* off = q_is_consistent ? nullptr : (F*)d_off;
+            if (off) rc = viprs_b200_q_offset_f64(ld, (F*)d_eta, (F*)d_q, (F)dq_scale, off, st);
+            if (rc == 0)
+                rc = K > 0 ? viprs_b200_e_step_mixture_f64(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
+                                                           (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, off, st)
+                           : viprs_b200_e_step_f64(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
+                                                   (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, off, st);
+        }
+    }
+    auto down = [&](void* dst, const void* src, size_t n) {
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+    };
+    down(var_gamma, d_g, ck); down(var_mu, d_mu, ck); down(eta, d_eta, c1); down(q, d_q, c1); down(eta_diff, d_diff, c1);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2;
+    if (rc) return rc;
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+// one-shot: upload + pack the LD, one sweep, destroy
 int host_dropin(int32_t M, int32_t K, const int32_t* lb, const void* indptr, int32_t is64, const void* ld_data,
                 int32_t ld_dtype, int32_t float_dtype, const void* std_beta, void* var_gamma, void* var_mu, void* eta,
                 void* q, void* eta_diff, const void* log_null_pi, const void* u_logs, const void* shvt,
@@ -39,49 +111,32 @@ int host_dropin(int32_t M, int32_t K, const int32_t* lb, const void* indptr, int
     viprs_b200_ld_t* ld = nullptr;
     int rc = viprs_b200_ld_create(&ld, M, lb, indptr, is64, ld_data, ld_dtype, VIPRS_B200_MEM_HOST, 0, nullptr);
     if (rc) return rc;
-    const size_t ts = float_dtype == VIPRS_B200_F32 ? 4 : 8;
-    const size_t kk = K > 0 ? (size_t)K : 1;
-    const size_t n1 = (size_t)M * ts, nk = n1 * kk;
-    // layout: [beta n1][eta n1][q n1][diff n1][lnp n1][gamma nk][mu nk][ulogs nk][shvt nk][mm nk]
-    DevBuf buf;
-    cudaError_t e = cudaMalloc(&buf.d, 5 * n1 + 5 * nk);
-    if (e != cudaSuccess) { viprs_b200_ld_destroy(ld); return (int)e; }
-    unsigned char* d = buf.d;
-    unsigned char *d_beta = d, *d_eta = d + n1, *d_q = d + 2 * n1, *d_diff = d + 3 * n1, *d_lnp = d + 4 * n1;
-    unsigned char *d_g = d + 5 * n1, *d_mu = d_g + nk, *d_ul = d_mu + nk, *d_sv = d_ul + nk, *d_mm = d_sv + nk;
-    auto up = [&](void* dst, const void* src, size_t n) {
-        if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, 0);
-    };
-    up(d_beta, std_beta, n1); up(d_eta, eta, n1); up(d_q, q, n1); up(d_diff, eta_diff, n1);
-    if (K > 0) up(d_lnp, log_null_pi, n1);
-    up(d_g, var_gamma, nk); up(d_mu, var_mu, nk); up(d_ul, u_logs, nk); up(d_sv, shvt, nk); up(d_mm, mu_mult, nk);
-    if (e == cudaSuccess) {
-        if (ts == 4) {
-            using F = float;
-            rc = K > 0 ? viprs_b200_e_step_mixture_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
-                                                       (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr)
-                       : viprs_b200_e_step_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
-                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr);
-        } else {
-            using F = double;
-            rc = K > 0 ? viprs_b200_e_step_mixture_f64(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff,
-                                                       (F*)d_lnp, (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr)
-                       : viprs_b200_e_step_f64(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
-                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, 1, nullptr);
-        }
-    }
-    auto down = [&](void* dst, const void* src, size_t n) {
-        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, 0);
-    };
-    down(var_gamma, d_g, nk); down(var_mu, d_mu, nk); down(eta, d_eta, n1); down(q, d_q, n1); down(eta_diff, d_diff, n1);
-    cudaError_t e2 = cudaStreamSynchronize(0);
-    if (e == cudaSuccess) e = e2;
+    rc = state_roundtrip(ld, K, float_dtype, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs, shvt,
+                         mu_mult, dq_scale, 0, nullptr);
     viprs_b200_ld_destroy(ld);
-    if (rc) return rc;
-    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+    return rc;
 }
 
 }  // namespace
+
+// cpp_e_step / cpp_e_step_mixture argument lists (e_step_cpp.pyx:91-105, 125-141) with HOST state arrays on a
+// device-resident LD matrix: what a per-iteration caller that keeps its state in numpy uses.
+extern "C" int viprs_b200_cpp_e_step_resident(const viprs_b200_ld_t* ld, int32_t float_dtype, const void* std_beta,
+                                              void* var_gamma, void* var_mu, void* eta, void* q, void* eta_diff,
+                                              const void* u_logs, const void* sqrt_half_var_tau, const void* mu_mult,
+                                              double dq_scale, int32_t q_is_consistent, void* stream) {
+    return state_roundtrip(ld, 0, float_dtype, std_beta, var_gamma, var_mu, eta, q, eta_diff, nullptr, u_logs,
+                           sqrt_half_var_tau, mu_mult, dq_scale, q_is_consistent, (cudaStream_t)stream);
+}
+extern "C" int viprs_b200_cpp_e_step_mixture_resident(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype,
+                                                      const void* std_beta, void* var_gamma, void* var_mu, void* eta,
+                                                      void* q, void* eta_diff, const void* log_null_pi, const void* u_logs,
+                                                      const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,
+                                                      int32_t q_is_consistent, void* stream) {
+    if (K < 1) return VIPRS_B200_EINVAL;
+    return state_roundtrip(ld, K, float_dtype, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
+                           sqrt_half_var_tau, mu_mult, dq_scale, q_is_consistent, (cudaStream_t)stream);
+}
 
 // cpp_e_step (e_step_cpp.pyx:91-122)
 extern "C" int viprs_b200_cpp_e_step(int32_t M, const int32_t* ld_left_bound, const void* ld_indptr,

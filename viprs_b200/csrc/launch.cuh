@@ -58,7 +58,7 @@ static int launch_one(const viprs_b200_ld* ld, const SweepPlan& p, const RingGeo
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
-        kern<<<ld->n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(pp, ma, sa);
+        kern<<<p.n_blocks, (NBW + 2) * WARP, g.smem_bytes, st>>>(pp, ma, sa);
     });
 }
 
@@ -74,7 +74,7 @@ static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
-        kern<<<ld->n_blocks, FAST_WARPS * WARP, FL.total, st>>>(pp, FL, ma, sa);
+        kern<<<p.n_blocks, FAST_WARPS * WARP, FL.total, st>>>(pp, FL, ma, sa);
     });
 }
 
@@ -84,13 +84,18 @@ static bool fast_path_ok(const viprs_b200_ld* ld) {
     return ld->max_block <= FAST_MAX_BLOCK && fast_ring_geometry(ld).nst >= 3 && env_int("VIPRS_B200_FORCE_GENERIC", 0) == 0;
 }
 
+// one launch over the sweep units of phase `ph` (all units when the LD has a single phase)
 template <typename T, typename U, typename Model>
-static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma, const StateArgs<T>& sa, cudaStream_t st) {
+static int launch_phase(const viprs_b200_ld* ld, int ph, const typename Model::Args& ma, const StateArgs<T>& sa, cudaStream_t st) {
     SweepPlan p;
     RingGeometry g;
+    const int first = ld->h_phase_ptr[ph], count = ld->h_phase_ptr[ph + 1] - first;
+    if (count <= 0) return VIPRS_B200_OK;
+    auto phase_of = [&](SweepPlan& q) { q.blk_order = ld->d_blk_order + first; q.n_blocks = count; };
     if constexpr (sizeof(T) == 4 && !Model::kHeavy && sizeof(U) != 8) {
         if (fast_path_ok<T, U, Model>(ld)) {
             make_plan(ld, (int)sizeof(T), p, g);        // ring fields are overridden by the fast launcher
+            phase_of(p);
             if (std::is_same<U, int8_t>::value && env_int("VIPRS_B200_LIMBS", 3) == 3)
                 return launch_fast_one<U, Model, 3>(ld, p, ma, sa, st);
             return launch_fast_one<U, Model, 4>(ld, p, ma, sa, st);
@@ -98,6 +103,7 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
     }
     int rc = make_plan(ld, (int)sizeof(T), p, g);
     if (rc) return rc;
+    phase_of(p);
     if constexpr (!Model::kHeavy) {
         if (g.ctas_per_sm >= 2) return launch_one<T, U, Model, 2>(ld, p, g, ma, sa, st);
     }
@@ -105,12 +111,91 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
 }
 
 template <typename T, typename U>
-static int launch_backward(const viprs_b200_ld* ld, const T* x, T* q, T dq, cudaStream_t st) {
+static int launch_backward_rows(int M, const void* rows, const int64_t* prow, const int32_t* pcs, const T* x, T* q, T dq,
+                                cudaStream_t st) {
     const int wpb = 8;
-    backward_dot_kernel<T, U><<<(ld->M + wpb - 1) / wpb, wpb * WARP, 0, st>>>(
-        ld->M, reinterpret_cast<const unsigned char*>(ld->d_packed), ld->d_prow, ld->d_pcs, x, q, dq);
+    backward_dot_kernel<T, U><<<(M + wpb - 1) / wpb, wpb * WARP, 0, st>>>(
+        M, reinterpret_cast<const unsigned char*>(rows), prow, pcs, x, q, dq);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+// q[j] += dq * sum_{k>j} R_jk x[k] over the in-unit rows and (tiled LD) the ext rows
+template <typename T, typename U>
+static int launch_backward(const viprs_b200_ld* ld, const T* x, T* q, T dq, cudaStream_t st) {
+    int rc = launch_backward_rows<T, U>(ld->M, ld->d_packed, ld->d_prow, ld->d_pcs, x, q, dq, st);
+    if (rc == 0 && ld->ext_elems > 0) rc = launch_backward_rows<T, U>(ld->M, ld->d_ext, ld->d_erow, ld->d_ecs, x, q, dq, st);
+    return rc;
+}
+
+// out[k] += scale * sum_j R_jk x[j] over `n_items` items (see forward_axpy_kernel); max_cols: widest item
+template <typename T, typename U>
+static int launch_forward(const int4* items, int n_items, int max_cols, const void* rows, const int64_t* prow,
+                          const int32_t* pcs, const T* x, T* out, T scale, cudaStream_t st) {
+    if (n_items <= 0 || max_cols <= 0) return VIPRS_B200_OK;
+    constexpr int EPV = LdTraits<U>::EPV;
+    dim3 grid((max_cols + FWD_THREADS * EPV - 1) / (FWD_THREADS * EPV), n_items);
+    forward_axpy_kernel<T, U><<<grid, FWD_THREADS, 0, st>>>(items, reinterpret_cast<const unsigned char*>(rows), prow, pcs,
+                                                           x, out, scale);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+template <typename T>
+__global__ void scale_copy_kernel(int M, const T* __restrict__ src, T scale, T* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) dst[i] = src ? src[i] * scale : T(0);
+}
+
+// One Gauss-Seidel sweep over every LD block.  LD blocks of up to kTileLimit rows are one sweep unit and one launch
+// covers them all.  Larger blocks are tiled (ld.cu): tile p of every block is swept by launch p with the strictly
+// sequential one-pass kernel, and the rectangles between tiles enter as two streaming matrix-vector products,
+//   bext[j]  = sum_{k in later tiles} R_jk eta_old[k]      (once, before anything is swept), and
+//   fext[k] += sum_{j in tile p}      R_jk eta_new[j]      (after launch p, for the columns of the later tiles),
+// so the order of the per-SNP updates -- and therefore the result -- is that of the reference's single chain.
+// q_offset (nullable, q units): a caller-supplied constant part of q (see viprs_b200_q_offset_*).
+template <typename T, typename U, typename Model>
+static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma, StateArgs<T> sa, const T* q_offset, T dq,
+                        cudaStream_t st) {
+    if (ld->n_phases == 1 && ld->ext_elems == 0) {
+        if (q_offset) { sa.fext = q_offset; sa.fscale = T(1) / dq; }
+        return launch_phase<T, U, Model>(ld, 0, ma, sa, st);
+    }
+    T* fext = reinterpret_cast<T*>(ld->d_fext);
+    T* bext = reinterpret_cast<T*>(ld->d_bext);
+    const int M = ld->M;
+    scale_copy_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(M, q_offset, T(1) / dq, fext);
+    cudaError_t e = cudaMemsetAsync(bext, 0, sizeof(T) * (size_t)M, st);
+    if (e != cudaSuccess) return (int)e;
+    int rc = launch_backward_rows<T, U>(M, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1), st);
+    sa.fext = fext; sa.bext = bext; sa.fscale = T(1);
+    for (int ph = 0; ph < ld->n_phases && rc == 0; ++ph) {
+        rc = launch_phase<T, U, Model>(ld, ph, ma, sa, st);
+        const int i0 = ld->h_ext_phase_ptr[ph], i1 = ld->h_ext_phase_ptr[ph + 1];
+        if (rc == 0 && i1 > i0)
+            rc = launch_forward<T, U>(ld->d_items_ext + i0, i1 - i0, ld->h_items_cols[ph], ld->d_ext, ld->d_erow, ld->d_ecs,
+                                      sa.eta, fext, T(1), st);
+    }
+    return rc;
+}
+
+// out = q - dq * (R - I) eta : the part of a caller's q that is NOT explained by eta.  The reference maintains q
+// incrementally (e_step.hpp:421,439), so whatever q holds beyond dq (R - I) eta on entry -- e.g. q = 0 next to
+// eta != 0 after a `param_0` warm start, VIPRS.py:339-357 -- stays in q for ever.  Passing this vector as
+// `q_offset` to the sweeps reproduces that.
+template <typename T, typename U>
+static int launch_q_offset(const viprs_b200_ld* ld, const T* eta, const T* q, T dq, T* out, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(out, q, sizeof(T) * (size_t)ld->M, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    int rc = launch_backward<T, U>(ld, eta, out, -dq, st);
+    if (rc == 0) rc = launch_forward<T, U>(ld->d_items_diag, ld->n_blocks, ld->h_items_cols[ld->n_phases], ld->d_packed,
+                                          ld->d_prow, ld->d_pcs, eta, out, -dq, st);
+    if (rc == 0 && ld->n_items_ext > 0) {
+        int mc = 0;
+        for (int p = 0; p < ld->n_phases; ++p) mc = ld->h_items_cols[p] > mc ? ld->h_items_cols[p] : mc;
+        rc = launch_forward<T, U>(ld->d_items_ext, ld->n_items_ext, mc, ld->d_ext, ld->d_erow, ld->d_ecs, eta, out, -dq, st);
+    }
+    return rc;
 }
 
 // dispatch over the LD storage type; F(U tag) -> int
@@ -130,23 +215,29 @@ static int for_ld_dtype(const viprs_b200_ld* ld, F&& f) {
 template <typename T>
 static int e_step_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
                            T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq,
-                           int materialize_q, cudaStream_t st) {
+                           int materialize_q, const T* q_offset, cudaStream_t st) {
     if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
         return VIPRS_B200_EINVAL;
     typename SlabModel<T>::Args ma{std_beta, u_logs, shvt, mu_mult, var_gamma, var_mu, dq};
     StateArgs<T> sa{eta, q, eta_diff};
     return for_ld_dtype<T>(ld, [&](auto tag) {
         using U = decltype(tag);
-        int rc = launch_sweep<T, U, SlabModel<T>>(ld, ma, sa, st);
+        int rc = launch_sweep<T, U, SlabModel<T>>(ld, ma, sa, q_offset, dq, st);
         if (rc == 0 && materialize_q) rc = launch_backward<T, U>(ld, eta, q, dq, st);
         return rc;
     });
 }
 
 template <typename T>
+static int q_offset_dispatch(const viprs_b200_ld* ld, const T* eta, const T* q, T dq, T* out, cudaStream_t st) {
+    if (!ld || !eta || !q || !out) return VIPRS_B200_EINVAL;
+    return for_ld_dtype<T>(ld, [&](auto tag) { return launch_q_offset<T, decltype(tag)>(ld, eta, q, dq, out, st); });
+}
+
+template <typename T>
 static int mixture_dispatch(const viprs_b200_ld* ld, int K, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
                             T* eta_diff, const T* log_null_pi, const T* u_logs, const T* shvt, const T* mu_mult, T dq,
-                            int materialize_q, cudaStream_t st) {
+                            int materialize_q, const T* q_offset, cudaStream_t st) {
     if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !log_null_pi || !u_logs || !shvt ||
         !mu_mult)
         return VIPRS_B200_EINVAL;
@@ -157,13 +248,13 @@ static int mixture_dispatch(const viprs_b200_ld* ld, int K, const T* std_beta, T
         int rc;
         if (K <= 4) {
             typename MixModel<T, 4>::Args ma{std_beta, u_logs, shvt, mu_mult, log_null_pi, var_gamma, var_mu, dq, K};
-            rc = launch_sweep<T, U, MixModel<T, 4>>(ld, ma, sa, st);
+            rc = launch_sweep<T, U, MixModel<T, 4>>(ld, ma, sa, q_offset, dq, st);
         } else if (K <= 8) {
             typename MixModel<T, 8>::Args ma{std_beta, u_logs, shvt, mu_mult, log_null_pi, var_gamma, var_mu, dq, K};
-            rc = launch_sweep<T, U, MixModel<T, 8>>(ld, ma, sa, st);
+            rc = launch_sweep<T, U, MixModel<T, 8>>(ld, ma, sa, q_offset, dq, st);
         } else {
             typename MixModel<T, 16>::Args ma{std_beta, u_logs, shvt, mu_mult, log_null_pi, var_gamma, var_mu, dq, K};
-            rc = launch_sweep<T, U, MixModel<T, 16>>(ld, ma, sa, st);
+            rc = launch_sweep<T, U, MixModel<T, 16>>(ld, ma, sa, q_offset, dq, st);
         }
         if (rc == 0 && materialize_q) rc = launch_backward<T, U>(ld, eta, q, dq, st);
         return rc;

@@ -111,7 +111,7 @@ extern "C" const char* viprs_b200_strerror(int code) {
         case VIPRS_B200_EINVAL: return "invalid argument";
         case VIPRS_B200_ELAYOUT: return "inconsistent LD layout (row run leaves [0, M) or negative length)";
         case VIPRS_B200_EBLOCK_TOO_LARGE:
-            return "an LD block does not fit the per-CTA shared-memory state (non-block / banded LD is not supported)";
+            return "grid sweep: an LD block is larger than 4096 SNPs (only the single-model and mixture sweeps tile larger blocks)";
         case VIPRS_B200_ENOMEM: return "out of memory";
         case VIPRS_B200_ENODEVICE: return "no CUDA device (there is no CPU fallback)";
         case VIPRS_B200_EUNSUPPORTED: return "unsupported dtype combination";
@@ -220,7 +220,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         // ---- per-row runs (strictly upper part), LD blocks ----------------------------------
         std::vector<int32_t> cs(M), ce(M), pcs(M);
         std::vector<int64_t> src_off(M), prow((size_t)M + 1);
-        std::vector<int32_t> blk_row;
+        std::vector<int32_t> ldblk_row;
         int64_t nnz = 0;
         int32_t runmax = 0;
         for (int j = 0; j < M; ++j) {
@@ -233,37 +233,74 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
             if (a >= b) { a = b = j + 1; }
             cs[j] = (int32_t)a; ce[j] = (int32_t)b; src_off[j] = ip[j] + skip;
             nnz += b - a;
-            if (j == 0 || runmax <= j) blk_row.push_back(j);   // no earlier row reaches column j
+            if (j == 0 || runmax <= j) ldblk_row.push_back(j);   // no earlier row reaches column j
             runmax = std::max<int32_t>(runmax, (int32_t)b);
+        }
+        ldblk_row.push_back(M);
+        const int nlb = (int)ldblk_row.size() - 1;
+
+        // ---- sweep units: an LD block, or kTileRows-row tiles of a block larger than kTileLimit -----------
+        std::vector<int32_t> blk_row, unit_phase;
+        int32_t max_ld_block = 0, n_phases = 1;
+        for (int b = 0; b < nlb; ++b) {
+            const int r0 = ldblk_row[b], r1 = ldblk_row[b + 1], B = r1 - r0;
+            max_ld_block = std::max(max_ld_block, B);
+            if (B <= vb::kTileLimit) {
+                blk_row.push_back(r0); unit_phase.push_back(0);
+            } else {
+                int ph = 0;
+                for (int t = r0; t < r1; t += vb::kTileRows) { blk_row.push_back(t); unit_phase.push_back(ph++); }
+                n_phases = std::max(n_phases, ph);
+            }
         }
         blk_row.push_back(M);
         const int nb = (int)blk_row.size() - 1;
 
-        // ---- aligned packed rows ------------------------------------------------------------
+        // ---- aligned packed rows (columns inside the unit) and ext rows (columns beyond it) ----------------
+        std::vector<int32_t> ce_in(M), ecs(M);
+        std::vector<int64_t> erow((size_t)M + 1);
         std::vector<int64_t> blk_cost(nb);
-        int64_t off = 0;
+        std::vector<int4> items_diag(nb);
+        std::vector<int32_t> unit_ext_end(nb, 0);
+        int64_t off = 0, eoff = 0;
         int32_t max_block = 0, max_row_bytes = 0;
         for (int b = 0; b < nb; ++b) {
             const int r0 = blk_row[b], r1 = blk_row[b + 1];
             max_block = std::max(max_block, r1 - r0);
             int64_t cost = 0;
             for (int j = r0; j < r1; ++j) {
+                const int32_t cin = std::min(ce[j], r1);             // end of the in-unit part
+                ce_in[j] = cin;
                 int32_t a = r0 + ((cs[j] - r0) / epv) * epv;
-                int32_t e = r0 + ((ce[j] - r0 + epv - 1) / epv) * epv;
-                if (ce[j] == cs[j]) { e = a; }
+                int32_t e = r0 + ((cin - r0 + epv - 1) / epv) * epv;
+                if (cin <= cs[j]) { a = r0 + ((std::min(cs[j], r1) - r0) / epv) * epv; e = a; }
                 pcs[j] = a; prow[j] = off;
                 max_row_bytes = std::max<int32_t>(max_row_bytes, (e - a) * esize);
                 off += (e - a); cost += (int64_t)(e - a) * esize + 256;
+                // ext part: columns [max(cs, r1), ce), aligned to epv relative to r1
+                const int32_t xs = std::max(cs[j], r1);
+                int32_t xa = r1, xe = r1;
+                if (ce[j] > xs) {
+                    xa = r1 + ((xs - r1) / epv) * epv;
+                    xe = r1 + ((ce[j] - r1 + epv - 1) / epv) * epv;
+                    unit_ext_end[b] = std::max(unit_ext_end[b], ce[j]);
+                }
+                ecs[j] = xa; erow[j] = eoff;
+                eoff += (xe - xa);
             }
             blk_cost[b] = cost;
+            items_diag[b] = make_int4(r0, r1, r0, r1);
         }
         prow[M] = off;
+        erow[M] = eoff;
 
         CUDA_TRY(cudaGetDevice(&h->device));
         CUDA_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
         h->M = M; h->ld_dtype = ld_dtype; h->esize = esize; h->epv = epv; h->nnz = nnz;
-        h->packed_elems = off; h->n_blocks = nb; h->max_block = max_block; h->max_row_bytes = max_row_bytes;
+        h->packed_elems = off; h->ext_elems = eoff; h->n_blocks = nb; h->max_block = max_block; h->max_row_bytes = max_row_bytes;
+        h->n_ld_blocks = nlb; h->max_ld_block = max_ld_block; h->n_phases = n_phases;
         h->h_blk_row = blk_row;
+        h->h_ldblk_row = ldblk_row;
         stage_bytes = vb::choose_stage_bytes(max_block, max_row_bytes, h->smem_optin, stage_bytes);
         h->stage_bytes = stage_bytes;
         if (vb::ring_geometry(h, 4).nst == 0 && vb::fast_ring_geometry(h).nst == 0) { rc = VIPRS_B200_EBLOCK_TOO_LARGE; goto fail; }
@@ -308,9 +345,30 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         panel_row.push_back(M);
         h->n_panels = np;
 
+        // launch p sweeps the units of phase p, most expensive first (LPT schedule for ragged sizes)
         std::vector<int32_t> order(nb);
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return blk_cost[a] > blk_cost[b]; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (unit_phase[a] != unit_phase[b]) return unit_phase[a] < unit_phase[b];
+            return blk_cost[a] > blk_cost[b];
+        });
+        h->h_phase_ptr.assign(n_phases + 1, 0);
+        for (int b = 0; b < nb; ++b) h->h_phase_ptr[unit_phase[b] + 1]++;
+        for (int p = 0; p < n_phases; ++p) h->h_phase_ptr[p + 1] += h->h_phase_ptr[p];
+        // ext rectangles grouped by the phase of the unit that owns their rows
+        std::vector<int4> items_ext;
+        h->h_ext_phase_ptr.assign(n_phases + 1, 0);
+        h->h_items_cols.assign(n_phases + 1, 0);
+        for (int p = 0; p < n_phases; ++p) {
+            for (int b = 0; b < nb; ++b) {
+                if (unit_phase[b] != p || unit_ext_end[b] <= blk_row[b + 1]) continue;
+                items_ext.push_back(make_int4(blk_row[b], blk_row[b + 1], blk_row[b + 1], unit_ext_end[b]));
+                h->h_items_cols[p] = std::max(h->h_items_cols[p], unit_ext_end[b] - blk_row[b + 1]);
+            }
+            h->h_ext_phase_ptr[p + 1] = (int32_t)items_ext.size();
+        }
+        h->n_items_ext = (int32_t)items_ext.size();
+        h->h_items_cols[n_phases] = max_block;
 
         // ---- device arrays ------------------------------------------------------------------
         CUDA_TRY(cudaMalloc(&h->d_packed, (size_t)std::max<int64_t>(off, 16) * esize + 64));
@@ -321,6 +379,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMalloc(&h->d_panel_row, sizeof(int32_t) * (np + 1)));
         CUDA_TRY(cudaMalloc(&h->d_panel_need, sizeof(int32_t) * std::max(np, 1)));
         CUDA_TRY(cudaMalloc(&h->d_blk_order, sizeof(int32_t) * nb));
+        CUDA_TRY(cudaMalloc(&h->d_items_diag, sizeof(int4) * nb));
         CUDA_TRY(cudaMalloc(&d_src_off, sizeof(int64_t) * (size_t)M));
         CUDA_TRY(cudaMalloc(&d_cs, sizeof(int32_t) * (size_t)M));
         CUDA_TRY(cudaMalloc(&d_ce, sizeof(int32_t) * (size_t)M));
@@ -331,9 +390,10 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMemcpyAsync(h->d_panel_row, panel_row.data(), sizeof(int32_t) * (np + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_panel_need, panel_need.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_blk_order, order.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_items_diag, items_diag.data(), sizeof(int4) * nb, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(int64_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_cs, cs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(d_ce, ce.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_ce, ce_in.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
 
         const void* d_src = ld_data;
         const int64_t total_in = ip[M];
@@ -345,24 +405,51 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
             }
             d_src = d_raw;
         }
-        {
+        auto pack = [&](const int32_t* a_cs, const int32_t* a_ce, const int64_t* a_prow, const int32_t* a_pcs, void* dst) {
             const int wpb = 8;
             dim3 grid((M + wpb - 1) / wpb), block(wpb * vb::WARP);
             switch (ld_dtype) {
                 case VIPRS_B200_I8:
-                    vb::pack_rows_kernel<int8_t><<<grid, block, 0, stream>>>(M, (const int8_t*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (int8_t*)h->d_packed);
+                    vb::pack_rows_kernel<int8_t><<<grid, block, 0, stream>>>(M, (const int8_t*)d_src, d_src_off, a_cs, a_ce, a_prow, a_pcs, (int8_t*)dst);
                     break;
                 case VIPRS_B200_I16:
-                    vb::pack_rows_kernel<int16_t><<<grid, block, 0, stream>>>(M, (const int16_t*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (int16_t*)h->d_packed);
+                    vb::pack_rows_kernel<int16_t><<<grid, block, 0, stream>>>(M, (const int16_t*)d_src, d_src_off, a_cs, a_ce, a_prow, a_pcs, (int16_t*)dst);
                     break;
                 case VIPRS_B200_F32:
-                    vb::pack_rows_kernel<float><<<grid, block, 0, stream>>>(M, (const float*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (float*)h->d_packed);
+                    vb::pack_rows_kernel<float><<<grid, block, 0, stream>>>(M, (const float*)d_src, d_src_off, a_cs, a_ce, a_prow, a_pcs, (float*)dst);
                     break;
                 default:
-                    vb::pack_rows_kernel<double><<<grid, block, 0, stream>>>(M, (const double*)d_src, d_src_off, d_cs, d_ce, h->d_prow, h->d_pcs, (double*)h->d_packed);
+                    vb::pack_rows_kernel<double><<<grid, block, 0, stream>>>(M, (const double*)d_src, d_src_off, a_cs, a_ce, a_prow, a_pcs, (double*)dst);
                     break;
             }
-            CUDA_TRY(cudaGetLastError());
+            return cudaGetLastError();
+        };
+        CUDA_TRY(pack(d_cs, d_ce, h->d_prow, h->d_pcs, h->d_packed));
+        if (eoff > 0) {
+            // the ext rows: same packing kernel, source columns [cs, ce) clipped to [unit end, ce)
+            CUDA_TRY(cudaMalloc(&h->d_ext, (size_t)eoff * esize + 64));
+            CUDA_TRY(cudaMalloc(&h->d_erow, sizeof(int64_t) * ((size_t)M + 1)));
+            CUDA_TRY(cudaMalloc(&h->d_ecs, sizeof(int32_t) * (size_t)M));
+            CUDA_TRY(cudaMalloc(&h->d_items_ext, sizeof(int4) * std::max<size_t>(items_ext.size(), 1)));
+            CUDA_TRY(cudaMalloc(&h->d_fext, 8 * (size_t)M));
+            CUDA_TRY(cudaMalloc(&h->d_bext, 8 * (size_t)M));
+            CUDA_TRY(cudaMemcpyAsync(h->d_erow, erow.data(), sizeof(int64_t) * ((size_t)M + 1), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_ecs, ecs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(h->d_items_ext, items_ext.data(), sizeof(int4) * items_ext.size(), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));      // d_cs / d_ce are re-used below
+            // pack_rows reads source element (col - cs[row]) + src_off[row] for cs <= col < ce: keep cs, raise nothing;
+            // the clip to [unit end, ce) comes from the destination range [ecs, ecs + len) and the test col >= xs
+            std::vector<int32_t> xs(M);
+            for (int b = 0; b < nb; ++b)
+                for (int j = blk_row[b]; j < blk_row[b + 1]; ++j) xs[j] = std::max(cs[j], blk_row[b + 1]);
+            // source offset of column xs[j]
+            std::vector<int64_t> xoff(M);
+            for (int j = 0; j < M; ++j) xoff[j] = src_off[j] + (xs[j] - cs[j]);
+            CUDA_TRY(cudaMemcpyAsync(d_src_off, xoff.data(), sizeof(int64_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(d_cs, xs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(d_ce, ce.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(pack(d_cs, d_ce, h->d_erow, h->d_ecs, h->d_ext));
+            CUDA_TRY(cudaStreamSynchronize(stream));
         }
         CUDA_TRY(cudaStreamSynchronize(stream));   // host vectors above are about to go out of scope
     }
@@ -379,6 +466,7 @@ fail:
 
 int vb::ensure_dense(const viprs_b200_ld* h, cudaStream_t stream) {
     if (h->d_dense) return VIPRS_B200_OK;
+    if (h->n_phases > 1 || h->ext_elems > 0) return VIPRS_B200_EBLOCK_TOO_LARGE;    // the grid sweep does not tile
     const int nb = h->n_blocks;
     std::vector<int64_t> off(nb);
     int64_t o = 0;
@@ -425,6 +513,8 @@ int vb::ensure_dense(const viprs_b200_ld* h, cudaStream_t stream) {
 extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     if (!h) return VIPRS_B200_OK;
     cudaFree(h->d_dense); cudaFree(h->d_dblk_off);
+    cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext);
+    cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
     cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);
     delete h;
@@ -433,6 +523,6 @@ extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
 
 extern "C" int viprs_b200_ld_block_rows(const viprs_b200_ld_t* h, int32_t* out_host) {
     if (!h || !out_host) return VIPRS_B200_EINVAL;
-    std::memcpy(out_host, h->h_blk_row.data(), sizeof(int32_t) * h->h_blk_row.size());
+    std::memcpy(out_host, h->h_ldblk_row.data(), sizeof(int32_t) * h->h_ldblk_row.size());
     return VIPRS_B200_OK;
 }

@@ -11,8 +11,11 @@ struct viprs_b200_ld {
     int32_t epv = 0;            // elements per 16-byte vector
     int64_t nnz = 0;            // strictly-upper stored entries kept (algorithmic elements)
     int64_t packed_elems = 0;   // elements in the aligned device layout
-    int32_t n_blocks = 0;
-    int32_t max_block = 0;      // rows of the largest LD block
+    int32_t n_blocks = 0;       // sweep units ("tiles"): one per LD block, or several for an LD block > kTileLimit rows
+    int32_t n_ld_blocks = 0;    // independent LD blocks found (maximal row ranges no earlier row reaches into)
+    int32_t n_phases = 1;       // max tiles per LD block: tile p of every block is swept in launch p (see below)
+    int32_t max_block = 0;      // rows of the largest sweep unit
+    int32_t max_ld_block = 0;   // rows of the largest LD block
     int32_t max_row_bytes = 0;  // longest packed row
     int32_t n_panels = 0;
     int32_t stage_bytes = 0;
@@ -29,9 +32,30 @@ struct viprs_b200_ld {
     int32_t* d_panel_row = nullptr;// [n_panels+1] first row of every panel
     int32_t* d_panel_need = nullptr;// [n_panels] panels of the block whose forward axpy must be complete
                                    //       before the chain warp may start this panel
-    int32_t* d_blk_order = nullptr;// [n_blocks] block ids, most expensive first (LPT schedule)
+    int32_t* d_blk_order = nullptr;// [n_blocks] unit ids grouped by phase, most expensive first inside a phase (LPT)
 
-    std::vector<int32_t> h_blk_row;  // host copy for callers (sharding across GPUs)
+    std::vector<int32_t> h_blk_row;     // host copy of the sweep-unit boundaries
+    std::vector<int32_t> h_ldblk_row;   // [n_ld_blocks+1] LD-block boundaries, for callers (sharding across GPUs)
+    std::vector<int32_t> h_phase_ptr;   // [n_phases+1] slice of d_blk_order swept by launch p
+
+    // ---- tiled LD blocks (blocks larger than kTileLimit rows, e.g. 10,240-SNP float64 blocks or banded LD) ----
+    // Row j of tile [t0, t1) keeps its columns (j, t1) in the packed layout above (the sequential part, swept by the
+    // one-pass kernels) and its columns [t1, row end) in the "ext" layout below: these rectangles enter the sweep as
+    // two streaming matrix-vector products, bext[j] = sum_k R_jk eta_old[k] before anything is swept and
+    // fext[k] += sum_j R_jk eta_new[j] after tile j's launch (DESIGN.md "tiled sweep").
+    void* d_ext = nullptr;         // [ext_elems] ext entries, rows 16B-aligned, biased integer codes
+    int64_t* d_erow = nullptr;     // [M+1] element offset of each ext row
+    int32_t* d_ecs = nullptr;      // [M]   first (aligned) column of each ext row, global index
+    int64_t ext_elems = 0;
+    int4* d_items_diag = nullptr;  // [n_blocks] {row0, row1, col0, col1} of every unit's packed triangle
+    int4* d_items_ext = nullptr;   // [n_items_ext] the same for every unit's ext rectangle, grouped by phase
+    int32_t n_items_ext = 0;
+    std::vector<int32_t> h_ext_phase_ptr;   // [n_phases+1] slice of d_items_ext belonging to phase p
+    std::vector<int32_t> h_items_cols;      // max columns of an item per phase / overall (grid sizing)
+    mutable void* d_host_ws = nullptr;   // staging of HOST state arrays (viprs_b200_cpp_e_step_resident), grown on demand
+    mutable int64_t host_ws_bytes = 0;
+    mutable void* d_fext = nullptr;   // [M] scratch of the state type (8 bytes per row): forward-external accumulator
+    mutable void* d_bext = nullptr;   // [M] scratch: backward-external dots
 
     // dense symmetric block layout for the grid sweep (built lazily by vb::ensure_dense): block b is a
     // B_b x Bp_b row-major matrix (Bp_b = B_b rounded up to 16 elements), zero diagonal, biased integer codes
@@ -41,6 +65,8 @@ struct viprs_b200_ld {
 };
 
 namespace vb {
+constexpr int kTileLimit = 4096;   // LD blocks up to this many rows are one sweep unit
+constexpr int kTileRows = 2048;    // tile size of larger blocks (fits the float64 state of the generic kernel)
 // shared memory per CTA that lets two CTAs share one SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr int kSmemTwoPerSM = 113 * 1024;
 struct RingGeometry { int nst; int smem_bytes; int ctas_per_sm; };

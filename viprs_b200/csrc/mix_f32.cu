@@ -5,7 +5,7 @@ extern "C" int viprs_b200_e_step_mixture_f32(const viprs_b200_ld_t* ld, int32_t 
                                              float* var_gamma, float* var_mu, float* eta, float* q, float* eta_diff,
                                              const float* log_null_pi, const float* u_logs,
                                              const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
-                                             int32_t materialize_q, void* stream) {
+                                             int32_t materialize_q, const float* q_offset, void* stream) {
     return vb::mixture_dispatch<float>(ld, K, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
-                                       sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, (cudaStream_t)stream);
+                                       sqrt_half_var_tau, mu_mult, dq_scale, materialize_q, q_offset, (cudaStream_t)stream);
 }

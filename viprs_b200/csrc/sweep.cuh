@@ -219,8 +219,14 @@ template <typename T> __device__ __forceinline__ T eps_of();
 template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920928955078125e-7f; }   // max(FLT_EPSILON, 1e-8)
 template <> __device__ __forceinline__ double eps_of<double>() { return 1e-8; }                    // max(DBL_EPSILON, 1e-8)
 
+// fext / bext (nullable): per-row external contributions to F_j + B_j, in LD-code units after scaling fext by fscale.
+//   fext: forward-type terms -- what earlier tiles of a tiled LD block contributed (sum_{i in earlier tiles} R_ij
+//         eta_i(new)), and/or the caller's q offset (q_in - dq (R - I) eta_in, in q units, fscale = 1 / dq); they are
+//         part of the q this sweep leaves behind.
+//   bext: backward-type terms of a tiled block (sum_{k in later tiles} R_jk eta_k(old)); like the in-tile backward dots
+//         they are NOT part of the forward q.
 template <typename T>
-struct StateArgs { T* eta; T* q; T* eta_diff; };
+struct StateArgs { T* eta; T* q; T* eta_diff; const T* fext = nullptr; const T* bext = nullptr; T fscale = T(1); };
 
 template <typename T> __device__ __forceinline__ void load_state_vec(const T* src, T* dst, int n16) {
     const uint4* sp = reinterpret_cast<const uint4*>(src);
@@ -370,6 +376,11 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
         Model::load_raw(ma, r0 + lane, false, pend);
     }
     T eo = (lane < B) ? sa.eta[r0 + lane] : T(0);
+    // external contributions of the lane's current / next column (tiled LD blocks, q offsets; see StateArgs)
+    const bool has_f = sa.fext != nullptr, has_b = sa.bext != nullptr;
+    auto load_fext = [&](int col) { return (has_f && col < B) ? mul_t(sa.fext[r0 + col], sa.fscale) : T(0); };
+    auto load_bext = [&](int col) { return (has_b && col < B) ? sa.bext[r0 + col] : T(0); };
+    T xf = load_fext(lane), xb = load_bext(lane), xf_pend = T(0), xb_pend = T(0);
     T X0 = T(0), X1 = T(0);
     const uint32_t a_rowmeta = smem_u32(sm.rowmeta), a_panelmeta = smem_u32(sm.panelmeta);
     int j0 = 0, s = 0;
@@ -392,7 +403,8 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             const int cl = j0 + rel;
 #pragma unroll
             for (int w = 0; w < NA; ++w) bsum += lds_t(a_partial + (uint32_t)(w * RR + (cl & (RR - 1))) * sizeof(T), T());
-            X0 += lds_t(a_f + (uint32_t)(cl & sm.fmask) * sizeof(T), T()) + bsum;
+            bsum += xb;                                          // backward part: in-tile dots + later tiles
+            X0 += lds_t(a_f + (uint32_t)(cl & sm.fmask) * sizeof(T), T()) + xf + bsum;
         }
         T Xown = T(0);
 #pragma unroll kChainUnroll
@@ -458,11 +470,12 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             if (sm.chain_rows != nullptr) st_release(sm.chain_rows, (uint32_t)(j0 + nrows));
         }
         trace_ev(p, lane, 8, 3, u);
-        if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; has_pend = false; }
+        if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; xf = xf_pend; xb = xb_pend; has_pend = false; }
         if (rel < nrows) {
             const int cn = j0 + rel + 32;
             Model::load_raw(ma, r0 + cn, cn < B, pend);
             eo_pend = (cn < B) ? sa.eta[r0 + cn] : T(0);                       // not yet rewritten: cn is >= 16 rows ahead
+            xf_pend = load_fext(cn); xb_pend = load_bext(cn);
             has_pend = true;
         }
         j0 += nrows;
@@ -792,7 +805,8 @@ __global__ void __launch_bounds__((NBW + 2) * WARP, MINB) sweep_kernel(const Swe
     }
 }
 
-// q[j] += dq * sum_{k>j} R_jk x[k]   (update_q_factor, e_step.hpp:307-338); one warp per row.
+// q[j] += dq * sum_{k>j} R_jk x[k]   (update_q_factor, e_step.hpp:307-338); one warp per row.  Works on any row
+// layout of ld.cu (packed in-unit rows, or the ext rows of a tiled block): `x` is indexed by global column.
 template <typename T, typename U>
 __global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ packed, const int64_t* __restrict__ prow,
                                     const int32_t* __restrict__ pcs, const T* __restrict__ x, T* __restrict__ q, T dq) {
@@ -802,6 +816,7 @@ __global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ pac
     const int lane = threadIdx.x % WARP;
     const int64_t o0 = prow[row];
     const int nv = (int)((prow[row + 1] - o0) / EPV);
+    if (nv == 0) return;
     const int c0 = pcs[row];
     const uint4* src = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
     typename Pk<T>::acc_t acc2 = Pk<T>::zero();
@@ -814,7 +829,59 @@ __global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ pac
         VecOps<T, U>::dot(c, xs, acc2);
     }
     const T acc = warp_sum(Pk<T>::sum(acc2));
-    if (lane == 0 && nv > 0) q[row] += dq * acc;
+    if (lane == 0) q[row] += dq * acc;
+}
+
+// out[k] += scale * sum_{j in [row0, row1)} R_jk x[j]  for the columns k in [col0, col1) of every item
+// {row0, row1, col0, col1}: the transposed product over a rectangle (or triangle) of stored rows.  Thread t of
+// chunk c owns LD vector c * FWD_THREADS + t of the item's column range (the row layouts of ld.cu are aligned to
+// 16 bytes relative to col0), walks the rows in order (fixed summation order: deterministic) and keeps its EPV
+// sums in registers.  Used for the forward-external accumulator of tiled LD blocks and for q offsets.
+constexpr int FWD_THREADS = 128;
+constexpr int FWD_MAX_ROWS = 4096;
+template <typename T, typename U>
+__global__ void __launch_bounds__(FWD_THREADS) forward_axpy_kernel(const int4* __restrict__ items,
+                                                                  const unsigned char* __restrict__ packed,
+                                                                  const int64_t* __restrict__ prow,
+                                                                  const int32_t* __restrict__ pcs,
+                                                                  const T* __restrict__ x, T* __restrict__ out, T scale) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    __shared__ T xs[FWD_MAX_ROWS];
+    __shared__ int64_t ro[FWD_MAX_ROWS / 4 + 1];       // row offsets / first columns of a 1024-row slab
+    __shared__ int32_t rc[FWD_MAX_ROWS / 4];
+    const int4 it = items[blockIdx.y];
+    const int row0 = it.x, row1 = it.y, col0 = it.z, col1 = it.w;
+    const int v = blockIdx.x * FWD_THREADS + threadIdx.x;
+    const int col = col0 + v * EPV;
+    if (col0 + (int)blockIdx.x * FWD_THREADS * EPV >= col1) return;          // whole CTA beyond the item (uniform)
+    for (int i = threadIdx.x; i < row1 - row0; i += FWD_THREADS) xs[i] = x[row0 + i];
+    T acc[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) acc[e] = T(0);
+    constexpr int SLAB = FWD_MAX_ROWS / 4;
+    for (int s0 = row0; s0 < row1; s0 += SLAB) {
+        const int ns = min(SLAB, row1 - s0);
+        __syncthreads();
+        for (int i = threadIdx.x; i <= ns; i += FWD_THREADS) ro[i] = prow[s0 + i];
+        for (int i = threadIdx.x; i < ns; i += FWD_THREADS) rc[i] = pcs[s0 + i];
+        __syncthreads();
+        if (col < col1) {
+#pragma unroll 4
+            for (int i = 0; i < ns; ++i) {
+                const int64_t o = ro[i];
+                const int rel = col - rc[i];
+                if (rel >= 0 && rel < (int)(ro[i + 1] - o)) {
+                    const uint4 c = __ldg(reinterpret_cast<const uint4*>(packed + (o + rel) * (int64_t)sizeof(U)));
+                    VecOps<T, U>::axpy(c, xs[s0 - row0 + i], acc);
+                }
+            }
+        }
+    }
+    if (col < col1) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            if (col + e < col1) out[col + e] = fma_t(scale, acc[e], out[col + e]);
+    }
 }
 
 }  // namespace vb

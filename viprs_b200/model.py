@@ -23,7 +23,7 @@ import torch
 
 from . import _lib, em_host
 from .em_host import MixHyper, SlabHyper
-from .e_step import e_step_device, e_step_grid_device, e_step_mixture_device
+from .e_step import e_step_device, e_step_grid_device, e_step_mixture_device, q_offset_device
 from .ld import DeviceLD, _stream_ptr
 from .optim import IterationConditionCounter, OptimizeResult
 from .parallel import SumsExchange, shard_genome, slice_chromosome
@@ -184,6 +184,7 @@ class VIPRS:
         self.initialize_theta(theta_0)
         self.initialize_variational_parameters(param_0)
         self.init_optim_meta()
+        self._upload_theta()          # elbo() / zeta / var_tau are usable straight after initialize(), as in the reference
 
     def init_optim_meta(self):
         self.history = {"ELBO": []}
@@ -212,8 +213,32 @@ class VIPRS:
         else:
             se = theta_0["sigma_epsilon"]
             tau = theta_0["tau_beta"] if "tau_beta" in theta_0 else (pi * M) / np.maximum(0.01, 1. - se)
+        if "lambda_min" in theta_0:                     # a grid over lambda_min reaches here through fix_params
+            self.lambda_min = float(theta_0["lambda_min"])
         ft = np.dtype(self.float_precision).type        # the reference casts pi / sigma_epsilon to float_precision (:311-314)
         self._hyp = SlabHyper(float(ft(pi)), float(ft(se)), float(tau), float(ft(self.lambda_min)))
+        self._sync_hyper()
+
+    def _sync_hyper(self):
+        """
+        Sharded fit: the random draws above come from each rank's own numpy RNG, so rank 0's hyper-parameters are
+        broadcast -- every shard must run the same model (the single-GPU model that rank 0 would have run).
+        """
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        h = self._hyp
+        parts = [np.atleast_1d(np.asarray(getattr(h, k), dtype=np.float64)).ravel()
+                 for k in ("pi", "sigma_epsilon", "tau_beta", "lambda_min")]
+        buf = torch.from_numpy(np.concatenate(parts)).to(self.device)
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(buf, src=src, group=self.group)
+        vals, o = buf.cpu().numpy(), 0
+        for k, part in zip(("pi", "sigma_epsilon", "tau_beta", "lambda_min"), parts):
+            v = vals[o:o + part.size]
+            o += part.size
+            cur = getattr(h, k)
+            setattr(h, k, v.copy() if isinstance(cur, np.ndarray) else float(v[0]))
 
     def _alloc_state(self):
         dev, T, M, nc = self.device, self._tdt, self.M, self._ncol
@@ -249,6 +274,14 @@ class VIPRS:
         self._theta_logtau = self._hyp.theta().copy()
         self._theta_logtau[:, 3] = 0.0                   # VIPRS.py:329,359: n / sigma_epsilon + tau_beta, no lambda
         self._sums = None
+        # The reference starts with q = 0 even when param_0 makes eta != 0 (VIPRS.py:355-357) and then maintains q
+        # incrementally, so q carries the constant offset -dq (R - I) eta_0 for the whole fit.  The one-pass sweep
+        # recomputes q from eta, so that offset is handed to it explicitly.
+        self._qoff = None
+        # (the batched grid sweep keeps q in/out incrementally, like the reference: nothing to do there)
+        if "mu" in param_0 and self.M > 0 and (self._layout == 1 or self._ncol == 1):
+            with torch.cuda.device(self.device):
+                self._qoff = q_offset_device(self.ld, self._eta, self._q, self.dequantize_scale)
 
     def _set_gamma_to_pi(self):
         self._g.fill_(float(self._hyp.pi[0]))
@@ -349,9 +382,10 @@ class VIPRS:
         _lib.check(rc, "viprs_b200_prepare")
 
     def _sweep(self):
+        # with a q offset the sum eta'q cannot use the 2 x forward-part identity: materialise q every iteration
         e_step_device(self.ld, self.std_beta_dev, self._g, self._mu, self._eta, self._q, self._diff, self._ul, self._tt,
-                      self._mm, self.dequantize_scale, False)
-        self._q_is_forward = True
+                      self._mm, self.dequantize_scale, self._qoff is not None, self._qoff)
+        self._q_is_forward = self._qoff is None
 
     def e_step(self):
         """VIPRS.e_step (VIPRS.py:381-424): pre-compute + one Gauss-Seidel sweep over every LD block."""
@@ -409,15 +443,17 @@ class VIPRS:
     def set_fixed_params(self, fix_params):
         """VIPRS.py:361-379."""
         self.fix_params.update(fix_params)
+        ft = np.dtype(self.float_precision).type         # the reference casts every fixed value (:372-379)
         for key, val in fix_params.items():
             if key == "sigma_epsilon":
-                self._hyp.sigma_epsilon[:] = val
+                self._hyp.sigma_epsilon[:] = float(ft(val))
             elif key == "tau_beta":
-                self._hyp.tau_beta[:] = val
+                self._hyp.tau_beta[:] = float(ft(val))
             elif key == "pi":
-                self._hyp.pi[:] = val
+                self._hyp.pi[:] = float(ft(val))
             elif key == "lambda_min":
-                self._hyp.lambda_min[:] = val
+                self.lambda_min = float(ft(val))         # survives a re-initialisation (MSE restart) like the reference's
+                self._hyp.lambda_min[:] = self.lambda_min
 
     def update_theta_history(self):
         """VIPRS.py:839-873 (the tracked quantities that exist on this path)."""
@@ -575,6 +611,7 @@ class VIPRSMix(VIPRS):
                 tau = d * (M * np.dot(1.0 / d, pis) / (1.0 - se))
         ft = np.dtype(self.float_precision).type
         self._hyp = MixHyper(np.asarray(pis).astype(ft).astype(np.float64), float(ft(se)), tau, d, float(ft(self.lambda_min)))
+        self._sync_hyper()
 
     def _alloc_state(self):
         super()._alloc_state()
@@ -606,8 +643,8 @@ class VIPRSMix(VIPRS):
 
     def _sweep(self):
         e_step_mixture_device(self.ld, self.std_beta_dev, self._g, self._mu, self._eta, self._q, self._diff, self._lnp,
-                              self._ul, self._tt, self._mm, self.dequantize_scale, False)
-        self._q_is_forward = True
+                              self._ul, self._tt, self._mm, self.dequantize_scale, self._qoff is not None, self._qoff)
+        self._q_is_forward = self._qoff is None
 
     def _theta_logtau_dev(self):
         # VIPRSMix.e_step never refreshes `_log_var_tau` (VIPRSMix.py:187-204 takes np.log(var_tau) inline), so the
@@ -638,6 +675,7 @@ class VIPRSMix(VIPRS):
             elif key == "pis":
                 self._hyp.pi = np.asarray(val, dtype=np.float64).copy()
             elif key == "lambda_min":
+                self.lambda_min = float(val)
                 self._hyp.lambda_min = float(val)
 
 
@@ -786,6 +824,11 @@ class VIPRSGrid(VIPRS):
                 sg_icc[g].update((i > min_iter) and np.isclose(self._hyp.sigma_g[g], prev_sigma_g[g], atol=x_abs_tol, rtol=0.)
                                  and med < x_abs_tol * 10, i)
                 dv_icc[g].update((curr < prev_elbo[g]) and not np.isclose(curr, prev_elbo[g], atol=1e3 * f_abs_tol, rtol=1e-4), i)
+                if mse_all[g] < 0. and not self._fix["sigma_epsilon"][g]:
+                    # VIPRS.py:1025-1038: re-initialise this model and refit it with sigma_epsilon fixed at 0.95
+                    logger.info(f"Iteration {i} | model {g}: MSE is negative; restarting with sigma_epsilon fixed.")
+                    self._restart_column(g, theta_0, param_0)
+                    continue
                 if mse_all[g] < 0.:
                     o.update(curr, stop_iteration=True, success=False, message=f"The MSE is negative ({mse_all[g]:.6f}).")
                 elif not np.isfinite(curr):
@@ -819,6 +862,29 @@ class VIPRSGrid(VIPRS):
         self._finish_validation(last_elbo)
         return self
 
+    def _restart_column(self, g, theta_0, param_0):
+        """The reference's MSE-negative restart (VIPRS.py:1025-1038) for one column of the batched grid."""
+        rec = dict(self._grid_records[g])
+        saved_fix, saved_hyp = self.fix_params, self._hyp
+        self.fix_params = dict(saved_fix, **rec)
+        VIPRS.initialize_theta(self, dict(theta_0 or {}))
+        one = self._hyp
+        self.fix_params, self._hyp = saved_fix, saved_hyp
+        self._hyp.pi[g], self._hyp.tau_beta[g], self._hyp.lambda_min[g] = one.pi[0], one.tau_beta[0], one.lambda_min[0]
+        self._hyp.sigma_epsilon[g] = .95
+        self._hyp.sigma_g[g] = 0.
+        self._fix["sigma_epsilon"][g] = True
+        self._mu[g].zero_(); self._q[g].zero_(); self._diff[g].zero_()
+        self._g[g].fill_(float(self._hyp.pi[g]))
+        for name, t in (("mu", self._mu), ("gamma", self._g)):
+            if param_0 and name in param_0:
+                for c, r0, r1 in zip(self.chromosomes, self._seg[:-1], self._seg[1:]):
+                    a, b = self.row_ranges[c]
+                    t[g, r0:r1].copy_(torch.as_tensor(np.asarray(param_0[name][c])[a:b], dtype=self._tdt).to(self.device))
+        self._eta[g].copy_(self._g[g] * self._mu[g])
+        self._theta_logtau[g] = [.95, self._hyp.tau_beta[g], self._hyp.pi[g], 0.0]
+        self._sums = None
+
     def _finish_validation(self, elbos):
         msgs = [o.message for o in self.optim_results]
         try:
@@ -835,19 +901,27 @@ class VIPRSGrid(VIPRS):
     def _fit_pathwise(self, restart=False, **fit_kwargs):
         G = self.n_models
         self._batched = False
-        cols = {k: [] for k in ("g", "mu", "q", "vt")}
+        cols = {k: [] for k in ("g", "mu", "q", "theta_last")}
         hyp = {k: np.empty(G) for k in ("sigma_epsilon", "pi", "sigma_g", "tau_beta")}
         elbos = np.empty(G)
         optim_results = []
         base_fix = dict(self.fix_params)
         for i, rec in enumerate(self._grid_records):
-            self.set_fixed_params(rec) if i > 0 and not restart else self.fix_params.update(rec)
+            # VIPRSGrid.py:197: set_fixed_params(params[i]) for EVERY i (lambda_min included); before the first fit
+            # there are no hyper-parameters to overwrite yet, initialize_theta picks the values up from fix_params
+            if hasattr(self, "_hyp") and self._hyp.ncol == 1:
+                self.set_fixed_params(rec)
+            else:
+                self.fix_params.update(rec)
+                if "lambda_min" in rec:
+                    self.lambda_min = float(np.dtype(self.float_precision).type(rec["lambda_min"]))
             VIPRS.fit(self, continued=(i > 0 and not restart), **fit_kwargs)
             optim_results.append(copy.deepcopy(self.optim_result))
             self.optim_result.reset()
             elbos[i] = self.history["ELBO"][-1]
             self._materialize_q()
             cols["g"].append(self._g.clone()); cols["mu"].append(self._mu.clone()); cols["q"].append(self._q.clone())
+            cols["theta_last"].append(self._theta_last[0].copy())      # var_tau of this model's last E-step (VIPRSGrid.py:219)
             hyp["sigma_epsilon"][i], hyp["pi"][i] = self._hyp.sigma_epsilon[0], self._hyp.pi[0]
             hyp["sigma_g"][i], hyp["tau_beta"][i] = self._hyp.sigma_g[0], self._hyp.tau_beta[0]
         self.fix_params = base_fix
@@ -861,7 +935,7 @@ class VIPRSGrid(VIPRS):
         self._g, self._mu, self._q = torch.stack(cols["g"]), torch.stack(cols["mu"]), torch.stack(cols["q"])
         self._eta = self._g * self._mu
         self._q_is_forward = False
-        self._theta_last = self._hyp.theta()
+        self._theta_last = np.stack(cols["theta_last"])
         self._sums = None
         self._active = list(range(G))
         self.pip = {c: v.cpu().numpy().copy() for c, v in self.compute_pip().items()}

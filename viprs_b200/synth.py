@@ -48,33 +48,43 @@ def dequantize_scale(ld_dtype):
     return 1.0
 
 
+def _block_draws(seed, block_id, B, k):
+    """The random numbers of LD block `block_id`: numpy Philox keyed on (seed, block_id), so that ANY subset of blocks
+    -- a CPU slice for the reference arm, one rank's shard of a multi-GPU run -- reproduces exactly the arrays of the
+    full genome, wherever the dense algebra below then runs."""
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), int(block_id)]))
+    return dict(Z=rng.standard_normal((B, k)), u=rng.random(B), b=rng.standard_normal(B), e1=rng.standard_normal(B),
+                e2=rng.standard_normal(k))
+
+
 def make_inputs(block_sizes, ld_dtype="float32", float_dtype=torch.float32, device="cpu", seed=SEED,
-                k=64, alpha=0.5, n=300000, h2=0.3, p_causal=0.01, symmetric=False):
+                k=64, alpha=0.5, n=300000, h2=0.3, p_causal=0.01, symmetric=False, block_ids=None, M_total=None):
     """
     Returns a dict of torch tensors on `device`:
       ld_data, ld_indptr (int64), ld_left_bound (int32), std_beta, n_per_snp, beta_true
     `symmetric=True` emits the `low_memory=False` layout instead (full block rows incl. diagonal).
+    `block_ids` (default 0 .. len-1) name the blocks for the per-block random streams; `M_total` is the genome size
+    the effect-size variance refers to (default: the sum of `block_sizes`) -- pass both to generate a shard.
     """
     dev = torch.device(device)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
     M = int(sum(block_sizes))
     udt = _LD_TORCH[ld_dtype]
     data, lens, lbs, betas, trues = [], [], [], [], []
     row0 = 0
-    sb2 = h2 / (p_causal * M)
-    for B in block_sizes:
-        Z = torch.randn(B, k, generator=gen, device=dev, dtype=torch.float64)
+    sb2 = h2 / (p_causal * (M_total or M))
+    ids = list(range(len(block_sizes))) if block_ids is None else list(block_ids)
+    f64 = lambda a: torch.from_numpy(a).to(dev)
+    for B, bid in zip(block_sizes, ids):
+        dr = _block_draws(seed, bid, B, k)
+        Z = f64(dr["Z"])
         C = (Z @ Z.T) / k
         dinv = torch.rsqrt(torch.diagonal(C))
         R = alpha * (C * dinv[:, None] * dinv[None, :])
         R.diagonal().add_(1.0 - alpha)
         R.diagonal().fill_(1.0)
-        causal = torch.rand(B, generator=gen, device=dev, dtype=torch.float64) < p_causal
-        bt = torch.randn(B, generator=gen, device=dev, dtype=torch.float64) * math.sqrt(sb2) * causal
-        e1 = torch.randn(B, generator=gen, device=dev, dtype=torch.float64)
-        e2 = torch.randn(k, generator=gen, device=dev, dtype=torch.float64)
-        eps = (math.sqrt(1 - alpha) * e1 + math.sqrt(alpha) * dinv * (Z @ e2) / math.sqrt(k)) / math.sqrt(n)
+        causal = f64(dr["u"]) < p_causal
+        bt = f64(dr["b"]) * math.sqrt(sb2) * causal
+        eps = (math.sqrt(1 - alpha) * f64(dr["e1"]) + math.sqrt(alpha) * dinv * (Z @ f64(dr["e2"])) / math.sqrt(k)) / math.sqrt(n)
         betas.append((R @ bt + eps))
         trues.append(bt)
         if ld_dtype == "int8":
@@ -93,19 +103,33 @@ def make_inputs(block_sizes, ld_dtype="float32", float_dtype=torch.float32, devi
             lens.append(torch.arange(B - 1, -1, -1, dtype=torch.int64, device=dev))
             lbs.append(torch.arange(row0 + 1, row0 + B + 1, dtype=torch.int32, device=dev))
         row0 += B
-    lens = torch.cat(lens)
+    lens = torch.cat(lens) if lens else torch.zeros(0, dtype=torch.int64, device=dev)
     indptr = torch.zeros(M + 1, dtype=torch.int64, device=dev)
     indptr[1:] = torch.cumsum(lens, 0)
+    cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=dev)
     return {
-        "ld_data": torch.cat(data),
+        "ld_data": cat(data, udt),
         "ld_indptr": indptr,
-        "ld_left_bound": torch.cat(lbs),
-        "std_beta": torch.cat(betas).to(float_dtype),
+        "ld_left_bound": cat(lbs, torch.int32),
+        "std_beta": cat(betas, torch.float64).to(float_dtype),
         "n_per_snp": torch.full((M,), float(n), dtype=torch.float64, device=dev),
-        "beta_true": torch.cat(trues),
+        "beta_true": cat(trues, torch.float64),
         "dq_scale": dequantize_scale(ld_dtype),
         "block_sizes": list(block_sizes),
     }
+
+
+def lognormal_sizes(M, median=650, sigma=0.6, lo=64, hi=4096, seed=SEED):
+    """LDetect-like genome-wide block sizes: log-normal around `median` SNPs (EUR LDetect has ~1,700 blocks for the
+    ~1.1 M HapMap3 SNPs), clipped to [lo, hi], summing to M."""
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), 2 ** 40]))
+    sizes, tot = [], 0
+    while tot < M:
+        s = int(np.clip(np.rint(np.exp(np.log(median) + sigma * rng.standard_normal())), lo, hi))
+        s = min(s, M - tot)
+        sizes.append(s)
+        tot += s
+    return sizes
 
 
 def e_step_inputs(std_beta, n_per_snp, pi, sigma_epsilon, tau_beta, lambda_min=0.0, float_dtype=torch.float32):
