@@ -111,11 +111,10 @@ static int launch_phase(const viprs_b200_ld* ld, int ph, const typename Model::A
 }
 
 template <typename T, typename U>
-static int launch_backward_rows(int M, const void* rows, const int64_t* prow, const int32_t* pcs, const T* x, T* q, T dq,
-                                cudaStream_t st) {
-    const int wpb = 8;
-    backward_dot_kernel<T, U><<<(M + wpb - 1) / wpb, wpb * WARP, 0, st>>>(
-        M, reinterpret_cast<const unsigned char*>(rows), prow, pcs, x, q, dq);
+static int launch_row_dots(const int4* items, int n_items, const void* rows, const int64_t* prow, const int32_t* pcs,
+                           const T* x, T* q, T dq, cudaStream_t st) {
+    if (n_items <= 0) return VIPRS_B200_OK;
+    row_dot_kernel<T, U><<<n_items, BWD_THREADS, 0, st>>>(items, reinterpret_cast<const unsigned char*>(rows), prow, pcs, x, q, dq);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
 }
@@ -123,8 +122,8 @@ static int launch_backward_rows(int M, const void* rows, const int64_t* prow, co
 // q[j] += dq * sum_{k>j} R_jk x[k] over the in-unit rows and (tiled LD) the ext rows
 template <typename T, typename U>
 static int launch_backward(const viprs_b200_ld* ld, const T* x, T* q, T dq, cudaStream_t st) {
-    int rc = launch_backward_rows<T, U>(ld->M, ld->d_packed, ld->d_prow, ld->d_pcs, x, q, dq, st);
-    if (rc == 0 && ld->ext_elems > 0) rc = launch_backward_rows<T, U>(ld->M, ld->d_ext, ld->d_erow, ld->d_ecs, x, q, dq, st);
+    int rc = launch_row_dots<T, U>(ld->d_items_bwd, ld->n_items_bwd, ld->d_packed, ld->d_prow, ld->d_pcs, x, q, dq, st);
+    if (rc == 0) rc = launch_row_dots<T, U>(ld->d_items_bwd_ext, ld->n_items_bwd_ext, ld->d_ext, ld->d_erow, ld->d_ecs, x, q, dq, st);
     return rc;
 }
 
@@ -167,7 +166,7 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
     scale_copy_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(M, q_offset, T(1) / dq, fext);
     cudaError_t e = cudaMemsetAsync(bext, 0, sizeof(T) * (size_t)M, st);
     if (e != cudaSuccess) return (int)e;
-    int rc = launch_backward_rows<T, U>(M, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1), st);
+    int rc = launch_row_dots<T, U>(ld->d_items_bwd_ext, ld->n_items_bwd_ext, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1), st);
     sa.fext = fext; sa.bext = bext; sa.fscale = T(1);
     for (int ph = 0; ph < ld->n_phases && rc == 0; ++ph) {
         rc = launch_phase<T, U, Model>(ld, ph, ma, sa, st);
@@ -190,10 +189,13 @@ static int launch_q_offset(const viprs_b200_ld* ld, const T* eta, const T* q, T 
     int rc = launch_backward<T, U>(ld, eta, out, -dq, st);
     if (rc == 0) rc = launch_forward<T, U>(ld->d_items_diag, ld->n_blocks, ld->h_items_cols[ld->n_phases], ld->d_packed,
                                           ld->d_prow, ld->d_pcs, eta, out, -dq, st);
-    if (rc == 0 && ld->n_items_ext > 0) {
-        int mc = 0;
-        for (int p = 0; p < ld->n_phases; ++p) mc = ld->h_items_cols[p] > mc ? ld->h_items_cols[p] : mc;
-        rc = launch_forward<T, U>(ld->d_items_ext, ld->n_items_ext, mc, ld->d_ext, ld->d_erow, ld->d_ecs, eta, out, -dq, st);
+    // the ext rectangles of different tiles of one LD block overlap in columns: one launch per phase (inside a phase
+    // every item belongs to a different LD block, so no two CTAs update the same column)
+    for (int ph = 0; ph < ld->n_phases && rc == 0; ++ph) {
+        const int i0 = ld->h_ext_phase_ptr[ph], i1 = ld->h_ext_phase_ptr[ph + 1];
+        if (i1 > i0)
+            rc = launch_forward<T, U>(ld->d_items_ext + i0, i1 - i0, ld->h_items_cols[ph], ld->d_ext, ld->d_erow, ld->d_ecs,
+                                      eta, out, -dq, st);
     }
     return rc;
 }

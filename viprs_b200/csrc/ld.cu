@@ -369,6 +369,18 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         }
         h->n_items_ext = (int32_t)items_ext.size();
         h->h_items_cols[n_phases] = max_block;
+        // row-dot items (update_q_factor / backward-external products): <= 64-row chunks of every unit
+        std::vector<int4> items_bwd, items_bwd_ext;
+        for (int b = 0; b < nb; ++b) {
+            const int r0 = blk_row[b], r1 = blk_row[b + 1];
+            for (int j = r0; j < r1; j += 64) {
+                const int je = std::min(j + 64, r1);
+                if (prow[je] > prow[j]) items_bwd.push_back(make_int4(j, je, r0, r1));
+                if (erow[je] > erow[j]) items_bwd_ext.push_back(make_int4(j, je, r1, unit_ext_end[b]));
+            }
+        }
+        h->n_items_bwd = (int32_t)items_bwd.size();
+        h->n_items_bwd_ext = (int32_t)items_bwd_ext.size();
 
         // ---- device arrays ------------------------------------------------------------------
         CUDA_TRY(cudaMalloc(&h->d_packed, (size_t)std::max<int64_t>(off, 16) * esize + 64));
@@ -380,6 +392,10 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMalloc(&h->d_panel_need, sizeof(int32_t) * std::max(np, 1)));
         CUDA_TRY(cudaMalloc(&h->d_blk_order, sizeof(int32_t) * nb));
         CUDA_TRY(cudaMalloc(&h->d_items_diag, sizeof(int4) * nb));
+        CUDA_TRY(cudaMalloc(&h->d_items_bwd, sizeof(int4) * std::max<size_t>(items_bwd.size(), 1)));
+        CUDA_TRY(cudaMalloc(&h->d_items_bwd_ext, sizeof(int4) * std::max<size_t>(items_bwd_ext.size(), 1)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_items_bwd, items_bwd.data(), sizeof(int4) * items_bwd.size(), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_items_bwd_ext, items_bwd_ext.data(), sizeof(int4) * items_bwd_ext.size(), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMalloc(&d_src_off, sizeof(int64_t) * (size_t)M));
         CUDA_TRY(cudaMalloc(&d_cs, sizeof(int32_t) * (size_t)M));
         CUDA_TRY(cudaMalloc(&d_ce, sizeof(int32_t) * (size_t)M));
@@ -513,7 +529,7 @@ int vb::ensure_dense(const viprs_b200_ld* h, cudaStream_t stream) {
 extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     if (!h) return VIPRS_B200_OK;
     cudaFree(h->d_dense); cudaFree(h->d_dblk_off);
-    cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext);
+    cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext); cudaFree(h->d_items_bwd); cudaFree(h->d_items_bwd_ext);
     cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
     cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);

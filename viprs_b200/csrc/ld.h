@@ -50,6 +50,9 @@ struct viprs_b200_ld {
     int4* d_items_diag = nullptr;  // [n_blocks] {row0, row1, col0, col1} of every unit's packed triangle
     int4* d_items_ext = nullptr;   // [n_items_ext] the same for every unit's ext rectangle, grouped by phase
     int32_t n_items_ext = 0;
+    int4* d_items_bwd = nullptr;   // row_dot_kernel items: <= 64-row chunks of every unit's packed rows ...
+    int4* d_items_bwd_ext = nullptr;   // ... and of every unit's ext rows
+    int32_t n_items_bwd = 0, n_items_bwd_ext = 0;
     std::vector<int32_t> h_ext_phase_ptr;   // [n_phases+1] slice of d_items_ext belonging to phase p
     std::vector<int32_t> h_items_cols;      // max columns of an item per phase / overall (grid sizing)
     mutable void* d_host_ws = nullptr;   // staging of HOST state arrays (viprs_b200_cpp_e_step_resident), grown on demand

@@ -832,6 +832,58 @@ __global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ pac
     if (lane == 0) q[row] += dq * acc;
 }
 
+// The same product as backward_dot_kernel, organised for bandwidth: one CTA per item {row0, row1, col0, col1} = up to
+// BWD_ROWS consecutive rows of one sweep unit (or of its ext rectangle) and the unit's column range.  x is staged
+// through shared memory in BWD_COLS-column chunks aligned to col0 (every row layout of ld.cu is 16-byte aligned
+// relative to it), so the dot reads it with 128-bit shared loads instead of per-element global gathers; one warp per
+// row, four LD vectors in flight per lane.
+constexpr int BWD_ROWS = 64;
+constexpr int BWD_COLS = 4096;
+constexpr int BWD_THREADS = 256;
+template <typename T, typename U>
+__global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __restrict__ items,
+                                                             const unsigned char* __restrict__ packed,
+                                                             const int64_t* __restrict__ prow,
+                                                             const int32_t* __restrict__ pcs, const T* __restrict__ x,
+                                                             T* __restrict__ q, T dq) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    __shared__ __align__(16) T xs[BWD_COLS];
+    __shared__ T racc[BWD_ROWS];
+    const int4 it = items[blockIdx.x];
+    const int row0 = it.x, row1 = it.y, col0 = it.z, col1 = it.w;
+    const int warp = threadIdx.x / WARP, lane = threadIdx.x % WARP;
+    if (threadIdx.x < BWD_ROWS) racc[threadIdx.x] = T(0);
+    // columns below the first row's run are never touched: start at the chunk that holds it
+    const int first_col = pcs[row0];
+    for (int cbase = col0 + ((first_col - col0) / BWD_COLS) * BWD_COLS; cbase < col1; cbase += BWD_COLS) {
+        __syncthreads();
+        const int ncol = min(BWD_COLS, col1 - cbase);
+        for (int i = threadIdx.x; i < BWD_COLS; i += BWD_THREADS) xs[i] = (i < ncol) ? x[cbase + i] : T(0);
+        __syncthreads();
+        for (int r = row0 + warp; r < row1; r += BWD_THREADS / WARP) {
+            const int64_t o0 = prow[r];
+            const int nv = (int)((prow[r + 1] - o0) / EPV);
+            const int c0 = pcs[r];
+            const int v_lo = max(0, (cbase - c0) / EPV), v_hi = min(nv, (cbase + BWD_COLS - c0) / EPV);
+            if (v_lo >= v_hi) continue;                                   // warp-uniform
+            const uint4* src = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
+            const T* xr = xs + (c0 - cbase);
+            typename Pk<T>::acc_t acc2 = Pk<T>::zero();
+#pragma unroll 4
+            for (int v = v_lo + lane; v < v_hi; v += WARP) {
+                const uint4 c = __ldg(src + v);
+                T xv[EPV];
+                load_state_vec(xr + (size_t)v * EPV, xv, EPV * (int)sizeof(T) / 16);
+                VecOps<T, U>::dot(c, xv, acc2);
+            }
+            const T acc = warp_sum(Pk<T>::sum(acc2));
+            if (lane == 0) racc[r - row0] += acc;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < row1 - row0) q[row0 + threadIdx.x] += dq * racc[threadIdx.x];
+}
+
 // out[k] += scale * sum_{j in [row0, row1)} R_jk x[j]  for the columns k in [col0, col1) of every item
 // {row0, row1, col0, col1}: the transposed product over a rectangle (or triangle) of stored rows.  Thread t of
 // chunk c owns LD vector c * FWD_THREADS + t of the item's column range (the row layouts of ld.cu are aligned to
