@@ -253,6 +253,21 @@ int viprs_b200_sums_f64(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, c
                         const double* theta_logtau, double q_scale, void* workspace, int64_t workspace_bytes,
                         double* sums, void* stream);
 
+/* viprs_b200_em_update: the scalar side of one EM iteration ON THE DEVICE -- VIPRS.m_step (VIPRS.py:426-484), elbo
+ * (:497-581), mse (:689-704), get_heritability (:780-785), VIPRSMix.update_pi / update_tau_beta (VIPRSMix.py:227-260) --
+ * from the reduced sums, in float64.  theta (see above) is rewritten in place for the next viprs_b200_prepare_*;
+ * theta_prev receives theta as this iteration's sweep saw it (var_tau of the outputs, VIPRS.py:888-897); per model
+ * column scalars[(iter % hist_len)][col][8] = {ELBO, mse, max |eta_diff|, h2, pi, tau_beta, sigma_epsilon, sigma_g}
+ * and the device counter *iter is incremented, so prepare -> sweep -> sums -> em_update can be replayed (e.g. as a CUDA
+ * graph) without a host round trip.  flags[col]: bit 0 pi fixed, bit 1 tau_beta fixed, bit 2 sigma_epsilon fixed
+ * (layout 1 = mixture, one model: flags[0] bit 0 'pis', bit 1 'tau_betas', bit 2 sigma_epsilon, bit 3 total 'pi' fixed at
+ * mix_fix_pi; mix_d = prior multipliers).  seg_sizes: SNPs per chromosome; n_snps their sum; n = max n_per_snp.
+ * world > 1: `sums` is the all-reduced table and max_onehot[world][nseg][ncol] carries the per-rank maxima. */
+int viprs_b200_em_update(int32_t nseg, int32_t ncol, int32_t layout, int32_t world, const double* sums,
+                         const double* max_onehot, const double* seg_sizes, const int32_t* flags, const double* mix_d,
+                         double n_snps, double n, double mix_fix_pi, double* theta, double* theta_prev, double* sigma_g,
+                         double* scalars, int32_t hist_len, int32_t* iter, void* stream);
+
 /* cpp_e_step_grid(...) (e_step_cpp.pyx:161-195) with host buffers; (M,G) arrays Fortran-order, active_model_idx
  * a host array of n_active column indices.  q is in/out. */
 int viprs_b200_cpp_e_step_grid(int32_t M, int32_t G, int32_t n_active, const int32_t* active_model_idx,

@@ -261,7 +261,167 @@ static int sums_dispatch(int M, int ncol, int layout, int nseg, const int32_t* s
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The scalar side of one EM iteration on the device: M-step, ELBO, MSE, heritability and the convergence scalar from
+// the reduced sums -- VIPRS.m_step (VIPRS.py:426-484), elbo (:497-581), mse (:689-704), get_heritability (:780-785);
+// VIPRSMix.update_pi / update_tau_beta (VIPRSMix.py:227-260).  Float64 throughout, one thread per model column (the
+// mixture is one model: thread 0).  With this kernel an EM iteration is prepare -> sweep -> sums -> update with no
+// host round trip: theta is rewritten in place for the next prepare, and the per-iteration scalars go to a history
+// ring the host reads whenever it wants to look (every iteration for the reference's exact stopping rules, or every
+// k iterations).
+// ---------------------------------------------------------------------------------------------------------------
+struct EmUpdateArgs {
+    const double* sums;        // [nseg][ncol][NS]; world > 1: the all-reduced table
+    const double* max_onehot;  // nullable: [world][nseg][ncol] maxima of |eta_diff| per rank (the summed MAX_DIFF slot is void)
+    const double* seg_sizes;   // [nseg] SNPs per chromosome (global)
+    const int32_t* flags;      // [ncol] bit 0: pi fixed, 1: tau_beta fixed, 2: sigma_epsilon fixed; mixture: flags[0] bit 0:
+                               //        'pis' fixed, 1: 'tau_betas' fixed, 2: sigma_epsilon fixed, 3: total 'pi' fixed
+    const double* mix_d;       // mixture: [K] prior multipliers
+    double* theta;             // [ncol][4] in/out: sigma_epsilon, tau_beta, pi, lambda_min
+    double* theta_prev;        // [ncol][4] out: theta as the sweep of this iteration saw it
+    double* sigma_g;           // [ncol] out (mixture: [0])
+    double* scalars;           // [hist_len][ncol][8] ring: ELBO, mse, max |eta_diff|, h2, pi, tau_beta, sigma_epsilon, sigma_g
+    int32_t* iter;             // device iteration counter (incremented by this kernel)
+    double n_snps, n, mix_fix_pi;
+    int nseg, ncol, world, layout, hist_len;
+};
+
+__global__ void em_update_kernel(const EmUpdateArgs a) {
+    const int nseg = a.nseg, ncol = a.ncol;
+    const int it = *a.iter;
+    double* out = a.scalars + (size_t)(it % a.hist_len) * ncol * 8;
+    auto S = [&](int sg, int c, int slot) { return a.sums[((size_t)sg * ncol + c) * NS + slot]; };
+    auto maxdiff = [&](int c) {
+        double m = 0.0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            if (a.max_onehot != nullptr) {
+                for (int r = 0; r < a.world; ++r) m = fmax(m, a.max_onehot[((size_t)r * nseg + sg) * ncol + c]);
+            } else {
+                m = fmax(m, S(sg, c, VIPRS_B200_S_MAX_DIFF));
+            }
+        }
+        return m;
+    };
+    if (a.layout == 0) {
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x) {
+            double se = a.theta[c * 4 + 0], tau = a.theta[c * 4 + 1], pi = a.theta[c * 4 + 2];
+            const double lam = a.theta[c * 4 + 3];
+            for (int k = 0; k < 4; ++k) a.theta_prev[c * 4 + k] = a.theta[c * 4 + k];
+            const int fl = a.flags[c];
+            double T[NS];
+            for (int s = 0; s < NS; ++s) T[s] = 0.0;
+            double pi_mean = 0.0, zeta_tot = 0.0, sg_sum = 0.0;
+            for (int sg = 0; sg < nseg; ++sg) {
+                for (int s = 0; s < NS; ++s) T[s] += S(sg, c, s);
+                const double zeta = S(sg, c, VIPRS_B200_S_GAMMA_MU2) + S(sg, c, VIPRS_B200_S_G_INV_TAU);
+                pi_mean += S(sg, c, VIPRS_B200_S_GAMMA) / a.seg_sizes[sg];      // dict_mean: mean of per-chromosome means
+                zeta_tot += zeta;
+                sg_sum += (1.0 + lam) * zeta + S(sg, c, VIPRS_B200_S_ETA_Q);      // VIPRS.py:454-457
+            }
+            pi_mean /= (double)nseg;
+            if (!(fl & 1)) pi = pi_mean;                                          // :434
+            if (!(fl & 2)) tau = pi * a.n_snps / zeta_tot;                        // :444
+            const double sigma_g = sg_sum;
+            if (!(fl & 4)) se = 1.0 - 2.0 * T[VIPRS_B200_S_BETA_ETA] + sigma_g;   // :466-471
+            double e = -log(2.0 * 3.141592653589793 * se);                        // :545
+            if (!(fl & 4)) e -= 1.0;                                              // :552
+            else e -= (1.0 / se) * (1.0 - 2.0 * T[VIPRS_B200_S_BETA_ETA] + sigma_g);   // :558
+            e *= 0.5 * a.n;                                                       // :560
+            e -= T[VIPRS_B200_S_G_LOGG] - log(pi) * T[VIPRS_B200_S_GCLIP];        // :562
+            e -= T[VIPRS_B200_S_NG_LOGNG] - log(1.0 - pi) * T[VIPRS_B200_S_NGCLIP];   // :563
+            e += 0.5 * (T[VIPRS_B200_S_GCLIP] * (1.0 + log(tau)) - T[VIPRS_B200_S_G_LOG_TAU]);   // :565
+            e -= 0.5 * tau * (T[VIPRS_B200_S_GAMMA_MU2] + T[VIPRS_B200_S_G_INV_TAU]);   // :568
+            const double zt = T[VIPRS_B200_S_GAMMA_MU2] + T[VIPRS_B200_S_G_INV_TAU];
+            const double mse = 1.0 - 2.0 * T[VIPRS_B200_S_BETA_ETA] + (sigma_g - zt + T[VIPRS_B200_S_ETA2]);   // :689-704
+            a.theta[c * 4 + 0] = se; a.theta[c * 4 + 1] = tau; a.theta[c * 4 + 2] = pi;
+            a.sigma_g[c] = sigma_g;
+            double* o = out + (size_t)c * 8;
+            o[0] = e; o[1] = mse; o[2] = maxdiff(c); o[3] = sigma_g / (sigma_g + se);
+            o[4] = pi; o[5] = tau; o[6] = se; o[7] = sigma_g;
+        }
+    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // sparse mixture: one model with K = ncol components (VIPRSMix.py:227-260 + VIPRS.py:454-471, 497-581)
+        const int K = ncol;
+        const int fl = a.flags[0];
+        double se = a.theta[0];
+        const double lam = a.theta[3];
+        for (int k = 0; k < 4 * K; ++k) a.theta_prev[k] = a.theta[k];
+        double pis[16], taus[16], zetas[16], gam[16];
+        double pi_sum_new = 0.0;
+        for (int k = 0; k < K; ++k) {
+            pis[k] = a.theta[k * 4 + 2]; taus[k] = a.theta[k * 4 + 1];
+            double g = 0.0, z = 0.0;
+            for (int sg = 0; sg < nseg; ++sg) {
+                g += S(sg, k, VIPRS_B200_S_GAMMA);
+                z += S(sg, k, VIPRS_B200_S_GAMMA_MU2) + S(sg, k, VIPRS_B200_S_G_INV_TAU);
+            }
+            gam[k] = g; zetas[k] = z; pi_sum_new += g;
+        }
+        if (!(fl & 1)) {
+            for (int k = 0; k < K; ++k) pis[k] = (fl & 8) ? a.mix_fix_pi * gam[k] / pi_sum_new : gam[k] / a.n_snps;   // :237-239
+        }
+        double pi_tot = 0.0, dz = 0.0, zsum = 0.0;
+        for (int k = 0; k < K; ++k) { pi_tot += pis[k]; dz += a.mix_d[k] * zetas[k]; zsum += zetas[k]; }
+        if (!(fl & 2)) {
+            const double t = pi_tot * a.n_snps / dz;                               // :257
+            for (int k = 0; k < K; ++k) taus[k] = fmax(a.mix_d[k] * t, 1.0);       // :258-260
+        }
+        double eq = 0.0, be = 0.0, e2 = 0.0, nglog = 0.0, ngc = 0.0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            eq += S(sg, 0, VIPRS_B200_S_ETA_Q); be += S(sg, 0, VIPRS_B200_S_BETA_ETA); e2 += S(sg, 0, VIPRS_B200_S_ETA2);
+            nglog += S(sg, 0, VIPRS_B200_S_NG_LOGNG); ngc += S(sg, 0, VIPRS_B200_S_NGCLIP);
+        }
+        const double sigma_g = (1.0 + lam) * zsum + eq;
+        if (!(fl & 4)) se = 1.0 - 2.0 * be + sigma_g;
+        double e = -log(2.0 * 3.141592653589793 * se);
+        if (!(fl & 4)) e -= 1.0;
+        else e -= (1.0 / se) * (1.0 - 2.0 * be + sigma_g);
+        e *= 0.5 * a.n;
+        double t1 = 0.0, t3 = 0.0, t4 = 0.0;
+        for (int k = 0; k < K; ++k) {
+            double glogg = 0.0, gclip = 0.0, glogtau = 0.0, gczeta = 0.0;
+            for (int sg = 0; sg < nseg; ++sg) {
+                glogg += S(sg, k, VIPRS_B200_S_G_LOGG); gclip += S(sg, k, VIPRS_B200_S_GCLIP);
+                glogtau += S(sg, k, VIPRS_B200_S_G_LOG_TAU); gczeta += S(sg, k, VIPRS_B200_S_GC_ZETA);
+            }
+            t1 += glogg - log(pis[k]) * gclip;
+            t3 += gclip * (1.0 + log(taus[k])) - glogtau;
+            t4 += taus[k] * gczeta;
+        }
+        e -= t1;
+        e -= nglog - log(1.0 - pi_tot) * ngc;
+        e += 0.5 * t3;
+        e -= 0.5 * t4;
+        const double mse = 1.0 - 2.0 * be + (sigma_g - zsum + e2);
+        for (int k = 0; k < K; ++k) { a.theta[k * 4 + 0] = se; a.theta[k * 4 + 1] = taus[k]; a.theta[k * 4 + 2] = pis[k]; }
+        a.sigma_g[0] = sigma_g;
+        double* o = out;
+        o[0] = e; o[1] = mse; o[2] = maxdiff(0); o[3] = sigma_g / (sigma_g + se);
+        o[4] = pi_tot; o[5] = taus[K - 1]; o[6] = se; o[7] = sigma_g;
+    }
+    // every thread has read *a.iter before any increment: the kernel is launched with ONE CTA
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.iter = it + 1;
+}
+
 }  // namespace vb
+
+extern "C" int viprs_b200_em_update(int32_t nseg, int32_t ncol, int32_t layout, int32_t world, const double* sums,
+                                    const double* max_onehot, const double* seg_sizes, const int32_t* flags,
+                                    const double* mix_d, double n_snps, double n, double mix_fix_pi, double* theta,
+                                    double* theta_prev, double* sigma_g, double* scalars, int32_t hist_len, int32_t* iter,
+                                    void* stream) {
+    if (nseg <= 0 || ncol <= 0 || !sums || !seg_sizes || !flags || !theta || !theta_prev || !sigma_g || !scalars || !iter ||
+        hist_len <= 0)
+        return VIPRS_B200_EINVAL;
+    if (layout != 0 && layout != 1) return VIPRS_B200_EINVAL;
+    if (layout == 1 && (ncol > 16 || !mix_d)) return VIPRS_B200_EINVAL;
+    vb::EmUpdateArgs a{sums, max_onehot, seg_sizes, flags, mix_d, theta, theta_prev, sigma_g, scalars, iter,
+                       n_snps, n, mix_fix_pi, nseg, ncol, world > 0 ? world : 1, layout, hist_len};
+    vb::em_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
 
 extern "C" int64_t viprs_b200_sums_workspace_bytes(int32_t M, int32_t ncol, int32_t nseg) {
     if (M <= 0 || ncol <= 0 || nseg <= 0) return 0;

@@ -63,19 +63,28 @@ static int launch_one(const viprs_b200_ld* ld, const SweepPlan& p, const RingGeo
 }
 
 // register-resident kernel (float32 state, LD blocks <= 4096 SNPs, two CTAs per SM)
-template <typename U, typename Model, int NLIMB>
-static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
+template <typename U, typename Model, int NLIMB, int VER>
+static int launch_fast_ver(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
                            const StateArgs<float>& sa, cudaStream_t st) {
     const RingGeometry g = fast_ring_geometry(ld);
     const FastLayout FL = make_fast_layout(ld->stage_bytes, g.nst);
     p.nst = g.nst;
     p.L.stages = FL.stages;
-    auto kern = sweep_fast_kernel<U, Model, NLIMB>;
+    auto kern = sweep_fast_kernel<U, Model, NLIMB, VER>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
         kern<<<p.n_blocks, FAST_WARPS * WARP, FL.total, st>>>(pp, FL, ma, sa);
     });
+}
+
+// VIPRS_B200_FAST = 1: the round-1 chain (window gathered per step, outputs written by the chain warp); 2 (default):
+// constant-stride window layout, outputs written by the producer warp
+template <typename U, typename Model, int NLIMB>
+static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
+                           const StateArgs<float>& sa, cudaStream_t st) {
+    if (env_int("VIPRS_B200_FAST", 2) == 1) return launch_fast_ver<U, Model, NLIMB, 1>(ld, p, ma, sa, st);
+    return launch_fast_ver<U, Model, NLIMB, 2>(ld, p, ma, sa, st);
 }
 
 template <typename T, typename U, typename Model>

@@ -607,6 +607,327 @@ __device__ __forceinline__ void window_panel_i8(uint32_t sbase, uint32_t a_rowme
     }
 }
 
+// =============================================================================================
+// Version 2 of the chain / helper roles of the register-resident kernel (sweep_fast.cuh, VER == 2)
+// =============================================================================================
+// Window coefficients, layout 2: wwin2[(row & 63) * 64 + (col & 63)] = R[row][col] for row < col < cut_row (and inside
+// the row's stored run), 0 for every other slot.  Row jl only reaches chain-owned columns < cut_jl <= 32 (jl / 32) + 64,
+// i.e. columns of its own 32-column block and of the next one, so the chain warp keeps exactly two accumulators per
+// lane (X0: its column of the current block, X1: of the next block), switches them at 32-row boundaries (warp-uniform)
+// and reads its two coefficients at addresses that advance by one constant stride per row -- no per-step address
+// arithmetic, no per-lane window sliding.
+constexpr int W2 = 64;            // slots per row in layout 2
+
+// int8 LD: 16 lanes per row, one aligned 32-bit load + one 128-bit store each; two rows per warp and pass.
+template <int NP_>
+__device__ __forceinline__ void window_panel2_i8(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, int jl0, int P,
+                                                 int part, int lane) {
+    static_assert(NP_ == 4 && PMAX == 16, "window_panel2_i8: 2 rows per part and pass");
+    const uint32_t sw = (uint32_t)lane & 15u, rsub = (uint32_t)lane >> 4;
+#pragma unroll 1
+    for (uint32_t it = 0; it < 2; ++it) {
+        if (8u * it + 2u * (uint32_t)part >= (uint32_t)P) break;            // warp-uniform
+        const uint32_t r = 2u * (uint32_t)part + rsub + 8u * it;
+        const bool ok = r < (uint32_t)P;
+        const uint32_t jl = (uint32_t)jl0 + (ok ? r : 0u);
+        const uint4 m = lds128(a_rowmeta + (jl & (RR - 1)) * 16u);
+        const uint32_t jl4 = jl & ~3u;
+        const uint32_t cb = jl4 + ((4u * sw - jl4) & 63u);                  // the column in [jl4, jl4 + 64) with slot 4 sw
+        const uint32_t word = lds_u32(sbase + m.x + cb);
+        const uint32_t cut = ((jl + WIN + 15u) / 16u) * 16u;
+        const uint32_t lim = min(cut, m.z * 16u);                           // chain-owned and stored: (jl, lim)
+        float2 p0, p1;
+        VecOps<float, int8_t>::pairs(word, p0, p1);
+        uint4 o;
+        o.x = (cb > jl) & (cb < lim) ? __float_as_uint(p0.x) : 0u;
+        o.y = (cb + 1u > jl) & (cb + 1u < lim) ? __float_as_uint(p0.y) : 0u;
+        o.z = (cb + 2u > jl) & (cb + 2u < lim) ? __float_as_uint(p1.x) : 0u;
+        o.w = (cb + 3u > jl) & (cb + 3u < lim) ? __float_as_uint(p1.y) : 0u;
+        if (ok) sts128(a_wwin + ((jl & (RR - 1)) * W2 + 4u * sw) * 4u, o);
+    }
+}
+
+// any LD type: lane l writes slots l and l + 32 of one row; rows part, part + NP_, ... of the panel
+template <typename U, int NP_>
+__device__ __forceinline__ void window_panel2(uint32_t sbase, uint32_t a_rowmeta, uint32_t a_wwin, uint32_t zaddr,
+                                              int jl0, int P, int part, int lane) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+#pragma unroll 1
+    for (int r = part; r < P; r += NP_) {
+        const uint32_t jl = (uint32_t)(jl0 + r);
+        const uint4 m = lds128(a_rowmeta + (jl & (RR - 1)) * 16u);
+        const uint32_t cut = ((jl + WIN + EPV - 1) / EPV) * EPV;
+        const uint32_t lim = min(cut, m.z * (uint32_t)EPV);
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t slot = (uint32_t)lane + 32u * h;
+            const uint32_t col = jl + ((slot - jl) & 63u);                  // the column in [jl, jl + 64) with this slot
+            const bool in = (col > jl) & (col < lim);
+            v[h] = lds_code<U>(in ? sbase + m.x + col * ES : zaddr);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) sts_t(a_wwin + ((jl & (RR - 1)) * W2 + (uint32_t)lane + 32u * h) * 4u, v[h]);
+    }
+}
+
+// shared-memory hand-off from the chain to the output role (rings indexed by block-local row & 63)
+struct OutRings {
+    uint32_t a_xown, a_bsum;      // X the row's update was computed from; backward part (in-tile dots + later tiles)
+    uint32_t* chain_panels;       // panels the chain has finished (release / acquire)
+    uint32_t* out_rows;           // rows whose outputs have been written (release / acquire)
+};
+
+template <typename T, typename Model, int NA, int NC>
+__device__ __forceinline__ void chain_role2(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
+                                            const SmemView<T>& sm, const OutRings& orr, int r0, int B, int pan0, int NP,
+                                            int lane) {
+    const int NST = p.nst;
+    const T eps = eps_of<T>();
+    const uint32_t a_partial = smem_u32(sm.partial), a_wwin = smem_u32(sm.wwin), a_alpha = smem_u32(sm.alpha),
+                   a_f = smem_u32(sm.fsrc);
+    typename Model::Lane L;
+    typename Model::Raw pend;
+    bool has_pend = false;
+    T eo_pend = T(0);
+    {
+        typename Model::Raw r;
+        Model::load_raw(ma, r0 + lane, lane < B, r);
+        Model::derive(ma, r, L);
+        Model::load_raw(ma, r0 + lane, false, pend);
+    }
+    T eo = (lane < B) ? sa.eta[r0 + lane] : T(0);
+    const bool has_f = sa.fext != nullptr, has_b = sa.bext != nullptr;
+    auto load_fext = [&](int col) { return (has_f && col < B) ? mul_t(sa.fext[r0 + col], sa.fscale) : T(0); };
+    auto load_bext = [&](int col) { return (has_b && col < B) ? sa.bext[r0 + col] : T(0); };
+    T xf = load_fext(lane), xb = load_bext(lane), xf_pend = T(0), xb_pend = T(0);
+    T X0 = T(0), X1 = T(0);
+    const uint32_t a_rowmeta = smem_u32(sm.rowmeta), a_panelmeta = smem_u32(sm.panelmeta);
+    int j0 = 0, s = 0;
+    int need_c = 0;
+    for (int u = 0; u < NP; ++u) {
+        trace_ev(p, lane, 8, 0, u);
+        wait_progress<NA, NC>(sm.prog, (uint32_t)(u + 1), (uint32_t)need_c, lane);
+        const int nrows = (int)lds128(a_panelmeta + s * 16).x;
+        need_c = (int)lds128(a_rowmeta + (j0 & (RR - 1)) * 16).w;
+        if (j0 + nrows > RR) wait_ge(orr.out_rows, (uint32_t)(j0 + nrows - RR));   // the output rings are RR rows deep
+        trace_ev(p, lane, 8, 1, u);
+        const int base = j0 & 31;
+        const int rel = (lane - base) & 31;
+        if (base == 0 && j0 > 0) { X0 = X1; X1 = T(0); }          // the panel opens the next 32-column block (warp-uniform)
+        T bsum = T(0);
+        if (rel < nrows) {
+            const int cl = j0 + rel;
+#pragma unroll
+            for (int w = 0; w < NA; ++w) bsum += lds_t(a_partial + (uint32_t)(w * RR + (cl & (RR - 1))) * sizeof(T), T());
+            bsum += xb;
+            const T v = lds_t(a_f + (uint32_t)(cl & sm.fmask) * sizeof(T), T()) + xf + bsum;
+            if ((base + rel) & 32) X1 += v; else X0 += v;        // a panel may straddle a 32-row boundary
+        }
+        T Xown = T(0);
+        // one SNP update; lanes other than the row's owner compute with a stale X0 and their result is unused
+        auto one_step = [&](int j, T w0, T w1) {
+            T en, d;
+            bool skip;
+            typename Model::Out o;
+            Model::step(L, X0, eo, eps, en, d, skip, o);
+            const int src = j & 31;
+            const bool mine = lane == src;
+            Xown = mine ? X0 : Xown;
+            const T a = shfl_t(en, src);
+            if (mine) sts_t(a_alpha + (uint32_t)(j & (RR - 1)) * sizeof(T), en);      // eta_new for the C warps
+            X0 = fma_t(w0, a, X0);                     // :421 restricted to the window
+            X1 = fma_t(w1, a, X1);
+        };
+        auto waddr = [&](int j) {                      // address of the lane's current-block coefficient of row j
+            return a_wwin + (uint32_t)(j & (RR - 1)) * (W2 * 4u) + (uint32_t)lane * 4u + ((j & 32) ? 128u : 0u);
+        };
+        if ((j0 & 3) == 0) {
+            // panels are cut at multiples of 4 rows wherever the rows are short enough (ld.cu): groups of 4 steps never
+            // straddle a 32-row boundary, the coefficients of a group are fetched up front at constant offsets
+#pragma unroll 1
+            for (int h = 0; h < nrows; h += 4) {
+                const int jg = j0 + h;
+                if ((jg & 31) == 0 && h > 0) { X0 = X1; X1 = T(0); }             // a 32-row boundary inside the panel
+                const uint32_t g0 = waddr(jg);
+                const uint32_t g1 = (jg & 32) ? g0 - 128u : g0 + 128u;
+                const bool full = h + 4 <= nrows;
+                T w0[4], w1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w0[i] = T(0); w1[i] = T(0);
+                    if (full || h + i < nrows) {
+                        w0[i] = lds_t(g0 + (uint32_t)i * (W2 * 4u), T());
+                        w1[i] = lds_t(g1 + (uint32_t)i * (W2 * 4u), T());
+                    }
+                }
+                if (full) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) one_step(jg + i, w0[i], w1[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (h + i < nrows) one_step(jg + i, w0[i], w1[i]);
+                }
+            }
+        } else {
+            // long rows (a stage holds fewer than four of them): panels of 1..3 rows start anywhere
+#pragma unroll 1
+            for (int h = 0; h < nrows; ++h) {
+                const int j = j0 + h;
+                if ((j & 31) == 0 && h > 0) { X0 = X1; X1 = T(0); }
+                const uint32_t g0 = waddr(j);
+                const uint32_t g1 = (j & 32) ? g0 - 128u : g0 + 128u;
+                one_step(j, lds_t(g0, T()), lds_t(g1, T()));
+            }
+        }
+        trace_ev(p, lane, 8, 2, u);
+        if (rel < nrows) {
+            const uint32_t slot = (uint32_t)((j0 + rel) & (RR - 1)) * sizeof(T);
+            sts_t(orr.a_xown + slot, Xown);
+            sts_t(orr.a_bsum + slot, bsum);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sm.cdone[s]);
+            st_release(orr.chain_panels, (uint32_t)(u + 1));
+        }
+        trace_ev(p, lane, 8, 3, u);
+        if (has_pend) { Model::derive(ma, pend, L); eo = eo_pend; xf = xf_pend; xb = xb_pend; has_pend = false; }
+        if (rel < nrows) {
+            const int cn = j0 + rel + 32;
+            Model::load_raw(ma, r0 + cn, cn < B, pend);
+            eo_pend = (cn < B) ? sa.eta[r0 + cn] : T(0);      // written by the output role only after the chain is past cn
+            xf_pend = load_fext(cn); xb_pend = load_bext(cn);
+            has_pend = true;
+        }
+        j0 += nrows;
+        if (++s == NST) s = 0;
+    }
+}
+
+// Producer + output role of version 2: issues the TMA panels like producer_role and, while it would otherwise wait
+// for a free stage, writes the outputs of the panels the chain has finished: the update of every row is re-evaluated
+// from the X the chain saved (same function, same inputs: same bits) and var_mu / var_gamma / eta / eta_diff / q go to
+// global memory from here, off the chain's serial path.
+template <typename T, typename U, typename Model>
+__device__ __forceinline__ void producer_out_role(const SweepPlan& p, const typename Model::Args& ma,
+                                                  const StateArgs<T>& sa, unsigned char* smem, int4* rowmeta,
+                                                  int4* panelmeta, uint64_t* full, uint64_t* empty, const OutRings& orr,
+                                                  int r0, int B, int pan0, int NP, int lane, int* rowbase,
+                                                  int4* panelmeta2) {
+    constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int ES = (int)sizeof(U);
+    const int NST = p.nst;
+    const unsigned char* gsrc = p.packed;
+    const T eps = eps_of<T>();
+    const T dq = ma.dq;
+    // ---- output state: parameters of the next panel to write are prefetched one panel ahead ----
+    int out_u = 0;
+    typename Model::Raw oraw;
+    T oeo = T(0);
+    int ors = 0, ore = 0;
+    auto prefetch_out = [&]() {
+        if (out_u >= NP) return;
+        ors = p.panel_row[pan0 + out_u]; ore = p.panel_row[pan0 + out_u + 1];
+        const bool ok = lane < ore - ors;
+        Model::load_raw(ma, ors + lane, ok, oraw);
+        oeo = ok ? sa.eta[ors + lane] : T(0);
+    };
+    prefetch_out();
+    auto drain = [&]() {
+        while (out_u < NP && ld_acquire(orr.chain_panels) >= (uint32_t)(out_u + 1)) {
+            const int P = ore - ors;
+            if (lane < P) {
+                typename Model::Lane L;
+                Model::derive(ma, oraw, L);
+                const uint32_t slot = (uint32_t)((ors - r0 + lane) & (RR - 1)) * sizeof(T);
+                const T Xown = lds_t(orr.a_xown + slot, T());
+                const T bsum = lds_t(orr.a_bsum + slot, T());
+                T en, d;
+                bool skip;
+                typename Model::Out o;
+                Model::step(L, Xown, oeo, eps, en, d, skip, o);
+                const int row = ors + lane;
+                Model::store(ma, row, skip, o);
+                if (!skip) sa.eta[row] = en;                                       // :431
+                sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
+                sa.q[row] = dq * (Xown - bsum);                                    // forward part of q
+            }
+            __syncwarp();
+            if (lane == 0) st_release(orr.out_rows, (uint32_t)(ore - r0));
+            ++out_u;
+            prefetch_out();
+        }
+    };
+    (void)B;
+    int s = 0, k = 0;
+    for (int v = 0; v < NP; ++v) {
+        const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
+        const int P = re - rs;
+        const int64_t obase = p.prow[rs];
+        const int64_t oend = p.prow[re];
+        int64_t o0 = 0, o1 = 0;
+        int c = 0;
+        if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
+        const int need_next = (v + 1 < NP) ? p.panel_need[pan0 + v + 1] : 0;
+        int vs = 0x7fffffff, ve = 0;
+        int lo = 0, hi = 0x7fffffff;
+        int4 m = make_int4(0, 0, 0, 0);
+        if (lane < P) {
+            const int nv = (int)(o1 - o0) / EPV;
+            const int vs_r = c / EPV;
+            m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
+            m.y = vs_r; m.z = vs_r + nv; m.w = need_next;
+            if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
+            lo = vs_r; hi = vs_r + nv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vs = min(vs, __shfl_xor_sync(0xffffffffu, vs, o));
+            ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
+            lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = min(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        const uint32_t bytes = (uint32_t)((oend - obase) * ES);
+        trace_ev(p, lane, 9, 0, v);
+        drain();
+        if (k > 0) {
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&empty[s], (k - 1) & 1)) {     // the try_wait suspends for its time hint: a cheap idle loop
+                drain();
+                if (++spins > kSpinLimit) __trap();
+            }
+        }
+        trace_ev(p, lane, 9, 1, v);
+        if (lane < P) {
+            rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
+            rowbase[(rs - r0 + lane) & (RR - 1)] = m.x;
+        }
+        if (lane == 0) {
+            panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
+            panelmeta2[s] = make_int4(lo, hi, 0, 0);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (bytes > 0) {
+                mbar_arrive_expect_tx(&full[s], bytes);
+                tma_load_1d(smem + p.L.stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
+            } else {
+                mbar_arrive(&full[s]);
+            }
+            trace_ev(p, lane, 9, 2, v);
+        }
+        if (++s == NST) { s = 0; ++k; }
+    }
+    uint32_t spins = 0;
+    while (out_u < NP) {
+        drain();
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the generic sweep kernel: any state type, any block size that fits; block state in shared memory
 // ---------------------------------------------------------------------------------------------

@@ -37,7 +37,8 @@ constexpr int HP = 258;                   // entries of the fixed-point prefix s
 constexpr int NLIMB_MAX = 4;
 
 struct FastLayout {
-    uint32_t stages, rowmeta, panelmeta, panelmeta2, rowbase, partial, alpha, wwin, fring, hc, zero, red, bars, counters, total;
+    uint32_t stages, rowmeta, panelmeta, panelmeta2, rowbase, partial, alpha, wwin, fring, hc, zero, red, xown, bsum, bars,
+        counters, total;
 };
 inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     FastLayout L;
@@ -49,13 +50,15 @@ inline FastLayout make_fast_layout(int stage_bytes, int nst) {
     L.rowbase = o;   o += RR * 4;                                  // rowmeta[].x alone: one LDS.128 = four rows
     L.partial = o;   o += NAW * RR * 4;
     L.alpha = o;     o += RR * 4;
-    L.wwin = o;      o += RR * WW * 4;
+    L.wwin = o;      o += RR * W2 * 4;               // version 2 layout (64 slots per row); version 1 uses 48 of them
+    L.xown = o;      o += RR * 4;                    // version 2: chain -> output role
+    L.bsum = o;      o += RR * 4;
     L.fring = o;     o += FR * 4;
     L.hc = o;        o += HP * 8;
     L.zero = o;      o += 32;
     L.red = L.partial;                   // prologue scratch, dead before the first partial is written
     L.bars = o;      o += 3 * NST_MAX * (uint32_t)sizeof(uint64_t);
-    L.counters = o;  o += (NAW + NWW + NCW) * (uint32_t)sizeof(uint32_t);
+    L.counters = o;  o += (NAW + NWW + NCW + 2) * (uint32_t)sizeof(uint32_t);     // + chain_panels, out_rows (version 2)
     L.total = o;
     return L;
 }
@@ -90,7 +93,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // 
     return d;
 }
 
-template <typename U, typename Model, int NLIMB>
+template <typename U, typename Model, int NLIMB, int VER>
 __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
                                                                               const typename Model::Args ma,
                                                                               const StateArgs<float> sa) {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     // ---- prologue ----------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], NCW); mbar_init(&sm.cdone[s], 1); }
-        for (int w = 0; w < NAW + NWW + NCW; ++w) sm.prog[w] = 0;
+        for (int w = 0; w < NAW + NWW + NCW + 2; ++w) sm.prog[w] = 0;
         fence_mbar_init();
     }
     for (int i = tid; i < FR; i += blockDim.x) fring[i] = 0.f;
@@ -218,11 +221,20 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     }
     __syncthreads();
 
+    [[maybe_unused]] OutRings orr;
+    orr.a_xown = sbase + FL.xown; orr.a_bsum = sbase + FL.bsum;
+    orr.chain_panels = sm.prog + NAW + NWW + NCW; orr.out_rows = sm.prog + NAW + NWW + NCW + 1;
     if (warp == FAST_PRODUCER_WARP) {
-        producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
-                         reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
+        if constexpr (VER == 2)
+            producer_out_role<T, U, Model>(p, ma, sa, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, orr, r0, B, pan0, NP,
+                                           lane, reinterpret_cast<int*>(smem + FL.rowbase),
+                                           reinterpret_cast<int4*>(smem + FL.panelmeta2));
+        else
+            producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
+                             reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
     } else if (warp == FAST_CHAIN_WARP) {
-        chain_role<T, Model, NAW, NCW, NWW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
+        if constexpr (VER == 2) chain_role2<T, Model, NAW, NCW>(p, ma, sa, sm, orr, r0, B, pan0, NP, lane);
+        else chain_role<T, Model, NAW, NCW, NWW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else if (ai >= 0) {
         // =============================== A: backward dots =====================================
         // Per panel every owned tile is classified (warp-uniform): dead (no row of the panel stores it), interior
@@ -244,8 +256,13 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
             const uint4 pm2 = lds128(a_pm2 + s * 16);
             const int P = pm.x, vmin = pm.y, vmax = pm.z, jl0 = pm.w;
             const int lo_all = (int)pm2.x, hi_all = (int)pm2.y;
-            if constexpr (DP4A) window_panel_i8<NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, jl0, P, wa, lane);
-            else window_panel<U, NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, zaddr_code, jl0, P, wa, lane);
+            if constexpr (VER == 2) {
+                if constexpr (DP4A) window_panel2_i8<NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, jl0, P, wa, lane);
+                else window_panel2<U, NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, zaddr_code, jl0, P, wa, lane);
+            } else {
+                if constexpr (DP4A) window_panel_i8<NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, jl0, P, wa, lane);
+                else window_panel<U, NAW>(sbase, sbase + FL.rowmeta, sbase + FL.wwin, zaddr_code, jl0, P, wa, lane);
+            }
             trace_ev(p, lane, wa, 3, u);
             const bool quad = ((jl0 | P) & 3) == 0;
             bool live[NVT], inter[NVT];
