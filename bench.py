@@ -165,8 +165,8 @@ def config_of(name, wl, scaling, world):
             "snps": int(sum(sizes)) * mult, "ld_blocks": len(sizes) * mult,
             "nnz": int(sum(b * (b - 1) // 2 for b in sizes)) * mult,
             "grid_columns": wl["G"], "mixture_components": wl["K"],
-            "step": "prepare + sweep + sums kernels, read-back of the reduced sums, scalar M-step"
-                    + (", one NCCL all-reduce" if world > 1 else "")}
+            "step": "device-resident EM iteration: prepare + sweep + sums + scalar M-step/ELBO kernels"
+                    + (" + one NCCL all-reduce" if world > 1 else "") + ", per-iteration scalars read back once per 64 steps"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -305,7 +305,7 @@ def profiled_traffic(name):
     return None, None
 
 
-def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist, want_e2e):
+def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist, want_e2e, use_graph=False):
     """Device-resident EM steps of one workload; returns the measurements (max over ranks)."""
     import torch
     tsize = 4 if wl["fp"] == "float32" else 8
@@ -332,16 +332,21 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
         sweep_ev.append((a, b))
     model._sweep = timed_sweep
     n_ph = int(model.ld.n_phases)
-    launches_per_step = 2 + (n_ph if n_ph == 1 else 2 * n_ph + 1)     # prepare + sums + sweep launches (tiled: + products)
+    launches_per_step = 3 + (n_ph if n_ph == 1 else 2 * n_ph + 1)     # prepare + sums + em_update + sweep launches (tiled: + products)
 
     ld_bytes = nnz * ESIZE[wl["ld_dtype"]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if ld_bytes < (256 << 20) else None
 
-    def step():
-        if flush is not None:
-            flush.zero_()          # inputs smaller than the 126 MB L2: evict them between steps
-        model.e_step()
-        model.m_step()             # sums kernel, (all-reduce), read-back of the reduced table, scalar M-step
+    # device-resident EM iterations (model.em_iterations): prepare -> sweep -> sums -> [all-reduce] -> scalar M-step / ELBO
+    # kernels back to back, the host reads the per-iteration scalars once per chunk of <= 64 iterations
+    if flush is not None:
+        model._iter_hook = flush.zero_       # inputs smaller than the 126 MB L2: evict them between steps
+
+    def run_steps(n):
+        while n > 0:
+            c = min(n, 64)
+            model.em_iterations(c, graph=use_graph)
+            n -= c
 
     def barrier():
         torch.cuda.synchronize()
@@ -349,8 +354,7 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step()
+    run_steps(warmup)
     barrier()
     sweep_ev.clear()
     sampler = ClockSampler(local_rank)
@@ -360,12 +364,18 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
     barrier()
     t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(steps):
-        step()
+    run_steps(steps)
     e1.record()
     barrier()
     t_host1 = time.perf_counter()
     clocks = sampler.stop(t_host0, t_host1)
+    if use_graph:
+        # CUDA events cannot bracket a kernel inside a replayed graph: time the sweep launches of a few plain-launch
+        # iterations right after the timed region instead (same kernels, same data)
+        sweep_ev.clear()
+        for _ in range(min(steps, 20)):
+            model.em_iterations(1, graph=False)
+        torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in sweep_ev]))
     stats = torch.tensor([total_ms, kern_ms], device="cuda", dtype=torch.float64)
@@ -378,7 +388,10 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
     model._sweep = orig_sweep
     out = {"value": M_all * G * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": kern_ms,
            "steps": steps, "snps": M_all, "ld_blocks": nb_all, "nnz": nnz_all, "snps_this_rank": M, "clocks": clocks,
-           "launches_per_step": launches_per_step, "flushed_l2": flush is not None}
+           "launches_per_step": launches_per_step, "flushed_l2": flush is not None,
+           "kernel_ms_source": "CUDA events around every sweep launch inside the timed region" if not use_graph else
+                               "CUDA events around the sweep launches of 20 plain-launch iterations right after the timed region "
+                               "(the timed region replays a CUDA graph)"}
     # roofline of the dominant kernel (the sweep): whole-job algorithmic bytes over the slowest rank's launch time
     peaks = {}
     try:
@@ -454,6 +467,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the EM iteration as a CUDA graph in the timed region")
     ap.add_argument("--no-extras", action="store_true", help="skip the c3 / c4 / c1 sub-measurements of the default run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -488,14 +502,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    main_res = run_workload(args.workload, wl, steps, warmup, rank, world, local_rank, scaling, dist, not args.no_e2e)
+    main_res = run_workload(args.workload, wl, steps, warmup, rank, world, local_rank, scaling, dist, not args.no_e2e,
+                            use_graph=args.graph)
 
     extras = {}
     if args.workload == "c2" and not args.no_extras:
         for nm in ("c3", "c4", "c1"):
             w = WORKLOADS[nm]
             try:
-                r = run_workload(nm, w, w["default_steps"] if nm != "c4" else 50, 3, rank, world, local_rank, scaling, dist, False)
+                r = run_workload(nm, w, w["default_steps"] if nm != "c4" else 50, 3, rank, world, local_rank, scaling, dist, False,
+                                 use_graph=args.graph)
                 extras[nm] = {"workload": nm + ": " + w["desc"], "value": r["value"], "unit": "SNP-updates/s",
                               "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"], "steps": r["steps"],
                               "frac": r["roofline"]["frac"], "fp32_pipe_frac": r["roofline"].get("fp32_pipe_frac"),
@@ -523,6 +539,7 @@ def main():
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": cfg, "roofline": main_res["roofline"], "cpu_baseline": cpu, "e2e": main_res.get("e2e"),
                 "gpu_launches": main_res["launches_per_step"] * steps, "clocks": main_res["clocks"], "run": run_info}
+        line["roofline"]["kernel_ms_source"] = main_res["kernel_ms_source"]
         if extras:
             line["workloads"] = extras
         print(json.dumps(line))

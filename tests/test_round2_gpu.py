@@ -308,3 +308,68 @@ def test_em_history_c2_slice(vb, oracle_built):
     for key, v in rec.items():
         assert v <= 1e-4, (key, v)
     assert relmax(m.post_mean_beta[1], o.eta[1]) <= 2e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device-resident EM iterations (scalar M-step / ELBO on the device, CUDA graph)
+# ---------------------------------------------------------------------------------------------------------
+def _small_data(seed=3, ld_dtype=np.int8):
+    T = np.float32
+    rng = np.random.default_rng(seed)
+    P = make_block_ld(rng, (300, 517, 64, 1200), ld_dtype, T)
+    n = np.floor(rng.uniform(4e4, 6e4, P["M"]))
+    half = 300 + 517
+    ip = P["indptr"]
+    # two "chromosomes" so that pi = mean of per-chromosome means is exercised
+    c1 = dict(ld_data=P["data"][:ip[half]], ld_indptr=ip[:half + 1], ld_left_bound=P["lb"][:half], std_beta=P["beta"][:half],
+              n_per_snp=n[:half])
+    c2 = dict(ld_data=P["data"][ip[half]:], ld_indptr=ip[half:] - ip[half], ld_left_bound=P["lb"][half:] - half,
+              std_beta=P["beta"][half:], n_per_snp=n[half:])
+    return {1: c1, 2: c2}
+
+
+@pytest.mark.parametrize("kind", ["viprs", "mix"])
+@pytest.mark.parametrize("graph_chunk", [4, 1])
+def test_device_loop_matches_host_loop(vb, kind, graph_chunk):
+    from viprs_b200.model import VIPRS, VIPRSMix
+    data = _small_data()
+    mk = (lambda: VIPRS(data=data, float_precision="float32", tracked_params=["pi", "sigma_epsilon", "tau_beta"])) if kind == "viprs" \
+        else (lambda: VIPRSMix(data=data, K=3, float_precision="float32"))
+    th = {"pi": 0.02, "sigma_epsilon": 0.8} if kind == "viprs" else {"pis": [0.01, 0.005, 0.005], "sigma_epsilon": 0.8}
+    a = mk().fit(max_iter=9, min_iter=20, theta_0=dict(th), f_abs_tol=0., x_abs_tol=0.)
+    b = mk().fit(max_iter=9, min_iter=20, theta_0=dict(th), f_abs_tol=0., x_abs_tol=0., device_loop=True, check_every=graph_chunk)
+    ea, eb = np.array(a.history["ELBO"]), np.array(b.history["ELBO"])
+    assert ea.shape == eb.shape == (10,)
+    assert np.max(np.abs(ea - eb) / np.abs(ea)) <= 1e-10
+    if kind == "viprs":
+        for k in ("pi", "sigma_epsilon", "tau_beta"):
+            assert np.allclose(a.history[k], b.history[k], rtol=1e-10, atol=0)
+    for c in (1, 2):
+        assert relmax(b.post_mean_beta[c], a.post_mean_beta[c]) <= 1e-6
+        assert relmax(b.pip[c], a.pip[c]) <= 1e-6
+        assert relmax(b.post_var_beta[c], a.post_var_beta[c]) <= 1e-6
+    assert b.optim_result.nit == a.optim_result.nit and b.optim_result.message == a.optim_result.message
+
+
+def test_device_iterations_grid_match_host_steps(vb):
+    from viprs_b200.model import VIPRSGrid
+    data = _small_data(seed=8)
+    grid = [{"pi": p, "sigma_epsilon": s} for s in (0.7, 0.9) for p in (0.005, 0.02, 0.1)]
+
+    def mk():
+        m = VIPRSGrid(data=data, grid=grid, float_precision="float32")
+        m._batched = True
+        m._init_grid_hyper({})
+        m.initialize_variational_parameters()
+        m._active = list(range(len(grid)))
+        return m
+    a, b = mk(), mk()
+    ref = []
+    for _ in range(5):
+        a.e_step(); a.m_step()
+        ref.append(np.stack([a.elbo(), a.mse(), a.max_eta_diff()], axis=1))
+    hist = b.em_iterations(5, graph=True)
+    got = hist[:, :, :3]
+    assert got.shape == (5, len(grid), 3)
+    assert np.max(np.abs(got - np.array(ref)) / np.maximum(np.abs(np.array(ref)), 1e-12)) <= 1e-9
+    assert np.allclose(b._hyp.tau_beta, a._hyp.tau_beta, rtol=1e-10)

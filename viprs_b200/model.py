@@ -259,6 +259,8 @@ class VIPRS:
         self._sums_dev = (self._exchange.table() if self.world > 1 else
                           torch.zeros((nseg, nc, _lib.NSUMS), dtype=torch.float64, device=dev))
         self._q_is_forward = False
+        self._dev_em_ready = False          # device-resident EM buffers / the captured graph refer to the old arrays
+        self._graph = None
 
     def initialize_variational_parameters(self, param_0=None):
         """VIPRS.py:318-359: mu = 0, gamma = pi, eta = gamma * mu, q = 0 (param_0 may override mu / gamma)."""
@@ -368,9 +370,10 @@ class VIPRS:
         self._theta_host.copy_(torch.from_numpy(th))
         self._theta_dev.copy_(self._theta_host, non_blocking=True)
 
-    def _prepare(self):
+    def _prepare(self, upload=True):
         """VIPRS.py:400-406,418 on the device."""
-        self._upload_theta()
+        if upload:
+            self._upload_theta()
         if self.M == 0:
             return
         L = _lib.lib()
@@ -440,6 +443,117 @@ class VIPRS:
     def max_eta_diff(self):
         return float(em_host.max_eta_diff(self._reduce())[0])
 
+    # ------------------------------------------------------------------------------------------
+    # device-resident EM iterations: prepare -> sweep -> sums -> [all-reduce] -> scalar M-step / ELBO
+    # with nothing crossing PCIe; the host looks at the per-iteration scalars only when it wants to
+    # ------------------------------------------------------------------------------------------
+    _HIST = 64           # device history ring (iterations)
+
+    def _em_flags(self):
+        f = np.zeros(self._ncol, dtype=np.int32)
+        f += 1 * ("pi" in self.fix_params) + 2 * ("tau_beta" in self.fix_params) + 4 * ("sigma_epsilon" in self.fix_params)
+        return f
+
+    def _setup_device_em(self):
+        dev, nc = self.device, self._ncol
+        self._seg_sizes_dev = torch.from_numpy(self._seg_sizes()).to(dev)
+        self._flags_dev = torch.from_numpy(self._em_flags()).to(dev)
+        d = getattr(self, "d", None)
+        self._mixd_dev = torch.from_numpy(np.asarray(d, dtype=np.float64)).to(dev) if (d is not None and self._layout == 1) else None
+        self._theta_prev_dev = torch.zeros((nc, 4), dtype=torch.float64, device=dev)
+        self._sigma_g_dev = torch.zeros(nc, dtype=torch.float64, device=dev)
+        self._scal_dev = torch.zeros((self._HIST, nc, 8), dtype=torch.float64, device=dev)
+        self._iter_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._graph = None
+        self._dev_em_ready = True
+
+    def _device_iteration(self):
+        """One EM iteration, launches only (stream-ordered; capturable)."""
+        L = _lib.lib()
+        hook = getattr(self, "_iter_hook", None)          # (bench.py: L2 flush between iterations of small workloads)
+        if hook is not None:
+            hook()
+        self._prepare(upload=False)
+        if self.M > 0:
+            self._sweep()
+            fn = L.viprs_b200_sums_f32 if self._tdt == torch.float32 else L.viprs_b200_sums_f64
+            rc = fn(self.M, self._ncol, self._layout, len(self.chromosomes), self._seg_dev.data_ptr(),
+                    self._g.data_ptr(), self._mu.data_ptr(), self._eta.data_ptr(), self._q.data_ptr(),
+                    self._diff.data_ptr(), self.std_beta_dev.data_ptr(), self.n_per_snp_dev.data_ptr(),
+                    self._theta_dev.data_ptr(), self._theta_logtau_dev(), 2.0 if self._q_is_forward else 1.0,
+                    self._ws.data_ptr(), self._ws.numel(), self._sums_dev.data_ptr(), _stream_ptr())
+            _lib.check(rc, "viprs_b200_sums")
+        else:
+            self._sums_dev.zero_()
+        table = self._exchange.reduce_on_device(self._sums_dev)
+        onehot = self._exchange.onehot().data_ptr() if self.world > 1 else None
+        fixpi = float(self.fix_params.get("pi", 0.0)) if self._layout == 1 else 0.0
+        rc = L.viprs_b200_em_update(len(self.chromosomes), self._ncol, self._layout, self.world, table.data_ptr(), onehot,
+                                    self._seg_sizes_dev.data_ptr(), self._flags_dev.data_ptr(),
+                                    self._mixd_dev.data_ptr() if self._mixd_dev is not None else None,
+                                    float(self.n_snps), float(self.n), fixpi, self._theta_dev.data_ptr(),
+                                    self._theta_prev_dev.data_ptr(), self._sigma_g_dev.data_ptr(), self._scal_dev.data_ptr(),
+                                    self._HIST, self._iter_dev.data_ptr(), _stream_ptr())
+        _lib.check(rc, "viprs_b200_em_update")
+
+    def em_iterations(self, k, graph=True):
+        """
+        Run ``k`` EM iterations entirely on the device and return their scalars as a (k, ncol, 8) float64 array
+        (ELBO, mse, max |eta_diff|, h2, pi, tau_beta, sigma_epsilon, sigma_g per iteration and model column): ONE
+        synchronisation and one small read-back for the k iterations.  ``graph=True`` replays the iteration as a CUDA
+        graph (captured on first use; falls back to plain launches if capture is not possible).  The host-side
+        hyper-parameters (``pi``, ``tau_beta``, ...) are refreshed from the device afterwards.
+        """
+        assert 0 < k <= self._HIST
+        with torch.cuda.device(self.device):
+            if not getattr(self, "_dev_em_ready", False):
+                self._setup_device_em()
+            self._flags_dev.copy_(torch.from_numpy(self._em_flags()))
+            self._upload_theta()
+            key = self._graph_key()
+            if getattr(self, "_graph_key_captured", None) != key:
+                self._graph, self._graph_key_captured = None, key      # the captured launches no longer describe this model
+            it0 = int(self._iter_dev.item())
+            remaining = k
+            if graph and self._graph is None:
+                self._device_iteration()                          # lazy initialisation happens outside the capture
+                remaining -= 1
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._device_iteration()
+                    self._graph = g
+                except Exception as ex:                           # pragma: no cover
+                    logger.warning(f"CUDA graph capture of the EM iteration failed ({ex!r}); using plain launches")
+                    torch.cuda.synchronize()
+                    self._graph = False
+            for _ in range(remaining):
+                if graph and self._graph:
+                    self._graph.replay()
+                else:
+                    self._device_iteration()
+            torch.cuda.synchronize()
+            it1 = int(self._iter_dev.item())
+            scal = self._scal_dev.cpu().numpy()
+            hist = np.stack([scal[i % self._HIST] for i in range(it0, it1)]) if it1 > it0 else np.zeros((0, self._ncol, 8))
+            self._pull_hyper()
+        self._sums = None
+        return hist
+
+    def _graph_key(self):
+        return (self._qoff is None,)
+
+    def _pull_hyper(self):
+        """Host copies of the hyper-parameters <- device theta (after device-resident iterations)."""
+        th = self._theta_dev.cpu().numpy()
+        self._theta_last = self._theta_prev_dev.cpu().numpy().copy()
+        sg = self._sigma_g_dev.cpu().numpy()
+        h = self._hyp
+        if self._layout == 1:
+            h.sigma_epsilon = float(th[0, 0]); h.tau_beta = th[:, 1].copy(); h.pi = th[:, 2].copy(); h.sigma_g = float(sg[0])
+        else:
+            h.sigma_epsilon[:] = th[:, 0]; h.tau_beta[:] = th[:, 1]; h.pi[:] = th[:, 2]; h.sigma_g[:] = sg
+
     def set_fixed_params(self, fix_params):
         """VIPRS.py:361-379."""
         self.fix_params.update(fix_params)
@@ -489,7 +603,18 @@ class VIPRS:
     # fit (VIPRS.py:909-1124)
     # ------------------------------------------------------------------------------------------
     def fit(self, max_iter=1000, theta_0=None, param_0=None, continued=False, disable_pbar=True, min_iter=3,
-            f_abs_tol=1e-6, x_abs_tol=1e-6, patience=10, **kwargs):
+            f_abs_tol=1e-6, x_abs_tol=1e-6, patience=10, device_loop=False, check_every=8, **kwargs):
+        """
+        VIPRS.fit (VIPRS.py:909-1124): same initialisation, same per-iteration order (e_step, m_step, objective), same
+        stopping rules and messages.
+
+        ``device_loop=False`` (default): every iteration's sums come back to the host, which runs the scalar M-step and
+        the checks -- the reference's control flow one to one.  ``device_loop=True``: iterations run on the device in
+        chunks of ``check_every`` (CUDA graph of prepare -> sweep -> sums -> [all-reduce] -> scalar M-step / ELBO, see
+        ``em_iterations``); the host applies the SAME rules to the recorded per-iteration scalars afterwards, so the
+        history, the iteration at which the fit is declared finished and the message are the reference's, while the
+        state may have advanced by up to ``check_every - 1`` further iterations (it only gets closer to the fixed point).
+        """
         if not continued:
             self.initialize(theta_0, param_0)
             start_idx = 1
@@ -502,32 +627,54 @@ class VIPRS:
             prev_elbo = self.elbo()
         prev_sigma_g = self._sigma_g
         sigma_g_icc, divergence_icc = IterationConditionCounter(), IterationConditionCounter()
-        for i in range(start_idx, start_idx + max_iter):
+        i = start_idx
+        last = start_idx + max_iter
+        pending = []                       # device loop: scalars of iterations already run but not yet examined
+        while i < last:
             if self.optim_result.stop_iteration:
                 break
-            self.e_step()
-            self.m_step()
-            self.update_theta_history()
-            max_eta_diff = self.max_eta_diff()
-            curr_elbo = self.history["ELBO"][-1]
-            sigma_g_icc.update((i > min_iter) and np.isclose(self._sigma_g, prev_sigma_g, atol=x_abs_tol, rtol=0.)
+            if device_loop:
+                if not pending:
+                    hist = self.em_iterations(min(max(int(check_every), 1), last - i))
+                    pending = [dict(elbo=float(r[0, 0]) if self._layout == 0 else float(r[0, 0]), mse=float(r[0, 1]),
+                                    max_eta_diff=float(r[0, 2]), h2=float(r[0, 3]), sigma_g=float(r[0, 7]),
+                                    sigma_epsilon=float(r[0, 6]), pi=float(r[0, 4]), tau_beta=float(r[0, 5])) for r in hist]
+                it = pending.pop(0)
+                self.history["ELBO"].append(it["elbo"])
+                for tt in self.tracked_params:
+                    if isinstance(tt, str) and tt in it:
+                        self.history[tt].append(it[tt])
+                    elif tt == "heritability":
+                        self.history["heritability"].append(it["h2"])
+            else:
+                self.e_step()
+                self.m_step()
+                self.update_theta_history()
+                it = dict(elbo=self.history["ELBO"][-1], mse=self.mse(), max_eta_diff=self.max_eta_diff(),
+                          h2=self.get_heritability(), sigma_g=self._sigma_g, sigma_epsilon=self.sigma_epsilon)
+            max_eta_diff, curr_elbo, h2, mse, sg = it["max_eta_diff"], it["elbo"], it["h2"], it["mse"], it["sigma_g"]
+            sigma_g_icc.update((i > min_iter) and np.isclose(sg, prev_sigma_g, atol=x_abs_tol, rtol=0.)
                                and max_eta_diff < x_abs_tol * 10, i)
             divergence_icc.update((curr_elbo < prev_elbo) and not np.isclose(curr_elbo, prev_elbo, atol=1e3 * f_abs_tol,
                                                                               rtol=1e-4), i)
-            h2 = self.get_heritability()
-            if self.mse() < 0.:
+            if mse < 0.:
                 if "sigma_epsilon" not in self.fix_params:
                     logger.info(f"Iteration {i} | MSE is negative; restarting with sigma_epsilon fixed.")
                     self.initialize_theta(theta_0)
                     self.initialize_variational_parameters(param_0)
                     self.fix_params["sigma_epsilon"] = .95
-                    self._hyp.sigma_epsilon[:] = .95
+                    if self._layout == 1:
+                        self._hyp.sigma_epsilon = .95
+                    else:
+                        self._hyp.sigma_epsilon[:] = .95
+                    pending = []
+                    i += 1
                     continue
                 self.optim_result.update(curr_elbo, stop_iteration=True, success=False,
-                                         message=f"The MSE is negative ({self.mse():.6f}).")
+                                         message=f"The MSE is negative ({mse:.6f}).")
             elif not np.isfinite(curr_elbo):
                 self.optim_result.update(curr_elbo, stop_iteration=True, success=False, message="Objective (ELBO) is undefined.")
-            elif self.sigma_epsilon < 0.:
+            elif it["sigma_epsilon"] < 0.:
                 self.optim_result.update(curr_elbo, stop_iteration=True, success=False,
                                          message="Residual variance estimate is negative.")
             elif h2 > 1. or h2 < 0.:
@@ -548,10 +695,11 @@ class VIPRS:
             else:
                 self.optim_result.update(curr_elbo)
             prev_elbo = curr_elbo
-            prev_sigma_g = self._sigma_g
+            prev_sigma_g = sg
+            i += 1
         self.update_posterior_moments()
         if not self.optim_result.stop_iteration:
-            self.optim_result.update(self.elbo(), stop_iteration=True, success=False,
+            self.optim_result.update(self.history["ELBO"][-1] if device_loop else self.elbo(), stop_iteration=True, success=False,
                                      message="Maximum iterations reached without convergence.\n"
                                              "You may need to run the model for more iterations.", increment=False)
         if not self.optim_result.success:
@@ -640,6 +788,12 @@ class VIPRSMix(VIPRS):
 
     def get_heritability(self):
         return float(em_host.heritability(self._hyp.sigma_g, self._hyp.sigma_epsilon))
+
+    def _em_flags(self):
+        f = np.zeros(self._ncol, dtype=np.int32)
+        f[0] = (1 * ("pis" in self.fix_params) + 2 * ("tau_betas" in self.fix_params) + 4 * ("sigma_epsilon" in self.fix_params)
+                + 8 * ("pi" in self.fix_params))
+        return f
 
     def _sweep(self):
         e_step_mixture_device(self.ld, self.std_beta_dev, self._g, self._mu, self._eta, self._q, self._diff, self._lnp,
@@ -751,13 +905,25 @@ class VIPRSGrid(VIPRS):
     def _sweep(self):
         if not self._batched:
             return super()._sweep()
-        act = torch.as_tensor(self._active, dtype=torch.int32, device=self.device)
+        key = tuple(self._active)
+        if getattr(self, "_act_key", None) != key:                # (built outside any CUDA-graph capture)
+            self._act_dev = torch.as_tensor(self._active, dtype=torch.int32, device=self.device)
+            self._act_key = key
+        act = self._act_dev
         if act.numel() == 0:
             return
         cm = lambda t: t.t()                              # (G, M) storage -> column-major (M, G) view
         e_step_grid_device(self.ld, self.std_beta_dev, cm(self._g), cm(self._mu), cm(self._eta), cm(self._q), cm(self._diff),
                            cm(self._ul), cm(self._tt), cm(self._mm), self.dequantize_scale, act)
         self._q_is_forward = False                        # the grid sweep keeps the reference's full q in place
+
+    def _graph_key(self):
+        return (self._batched, tuple(self._active) if self._batched else (), self._qoff is None)
+
+    def _em_flags(self):
+        if not self._batched:
+            return super()._em_flags()
+        return (1 * self._fix["pi"] + 2 * self._fix["tau_beta"] + 4 * self._fix["sigma_epsilon"]).astype(np.int32)
 
     pi = property(lambda self: self._hyp.pi.copy() if self._batched or self._hyp.ncol > 1 else float(self._hyp.pi[0]))
     tau_beta = property(lambda self: self._hyp.tau_beta.copy() if self._batched or self._hyp.ncol > 1 else float(self._hyp.tau_beta[0]))

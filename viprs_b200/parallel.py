@@ -122,6 +122,27 @@ class SumsExchange:
         """(nseg, ncol, nsums) view of the send buffer: let the sums kernel write here and all_reduce() copies nothing."""
         return self.send[:self.n_main].view(self.nseg, self.ncol, self.nsums)
 
+    def onehot(self):
+        """(world, nseg, ncol) view of the reduced per-rank maxima (valid after reduce_on_device)."""
+        return self.recv[self.n_main:].view(self.world, self.nseg, self.ncol)
+
+    def reduce_on_device(self, sums):
+        """
+        The collective alone, nothing read back: returns the (nseg, ncol, nsums) device table every rank's
+        viprs_b200_em_update consumes (its MAX_DIFF slot is void for world > 1: use onehot()).  Stream-ordered, so it
+        can be captured into a CUDA graph together with the kernels around it.
+        """
+        if self.world == 1:
+            return sums
+        import torch.distributed as dist
+        main = self.table()
+        if sums.data_ptr() != main.data_ptr():
+            main.copy_(sums.view(self.nseg, self.ncol, self.nsums))
+        self.send[self.n_main:].view(self.world, self.nseg, self.ncol)[self.rank].copy_(main[:, :, self.max_slot])
+        self.recv.copy_(self.send)
+        dist.all_reduce(self.recv, op=dist.ReduceOp.SUM, group=self.group)
+        return self.recv[:self.n_main].view(self.nseg, self.ncol, self.nsums)
+
     def all_reduce(self, sums):
         """sums: (nseg, ncol, nsums) float64 tensor (device of the exchange) -> reduced numpy array."""
         if self.world == 1:
