@@ -257,7 +257,13 @@ def build_model(name, wl, rank, world, scaling):
     from viprs_b200.model import VIPRS, VIPRSGrid, VIPRSMix
     sizes = genome_sizes(wl, world)
     Mg = int(sum(sizes))
-    if scaling == "strong":
+    if wl.get("per_rank_blocks"):
+        # defined per GPU (c5: 30 GB of float64 LD each): rank r holds blocks [r p, (r + 1) p) of the genome
+        b0 = min(rank * wl["per_rank_blocks"], len(sizes))
+        b1 = min(b0 + wl["per_rank_blocks"], len(sizes))
+        ids = list(range(b0, b1))
+        mine = sizes[b0:b1]
+    elif scaling == "strong":
         b0, b1 = shard_blocks(sizes, rank, world)
         ids = list(range(b0, b1))
         mine = sizes[b0:b1]
@@ -499,6 +505,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
