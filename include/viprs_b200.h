@@ -253,6 +253,17 @@ int viprs_b200_sums_f64(int32_t M, int32_t ncol, int32_t layout, int32_t nseg, c
                         const double* theta_logtau, double q_scale, void* workspace, int64_t workspace_bytes,
                         double* sums, void* stream);
 
+/* viprs_b200_e_step_fused_f32: viprs_b200_e_step_f32 (materialize_q = 0, no q_offset) with the reductions of
+ * viprs_b200_sums_f32 (ncol = 1, layout 0, q_scale = 2, theta_logtau = theta) FUSED into the sweep: the warp that writes a
+ * row's outputs also accumulates its VIPRS_B200_S_* terms (float64, fixed order), one table row per LD block, folded per
+ * chromosome segment by a one-CTA-per-segment kernel -- the per-SNP arrays are not read a second time.  theta / n_per_snp /
+ * seg_ptr / sums as in viprs_b200_sums_f32.  Returns VIPRS_B200_EUNSUPPORTED for configurations the fused kernel does not
+ * cover (float64 LD, LD blocks the register-resident kernel cannot take): run the sweep and the sums separately then. */
+int viprs_b200_e_step_fused_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma, float* var_mu, float* eta,
+                                float* q, float* eta_diff, const float* u_logs, const float* sqrt_half_var_tau,
+                                const float* mu_mult, float dq_scale, const double* n_per_snp, const double* theta,
+                                int32_t nseg, const int32_t* seg_ptr, double* sums, void* stream);
+
 /* viprs_b200_em_update: the scalar side of one EM iteration ON THE DEVICE -- VIPRS.m_step (VIPRS.py:426-484), elbo
  * (:497-581), mse (:689-704), get_heritability (:780-785), VIPRSMix.update_pi / update_tau_beta (VIPRSMix.py:227-260) --
  * from the reduced sums, in float64.  theta (see above) is rewritten in place for the next viprs_b200_prepare_*;

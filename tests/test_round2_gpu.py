@@ -373,3 +373,57 @@ def test_device_iterations_grid_match_host_steps(vb):
     assert got.shape == (5, len(grid), 3)
     assert np.max(np.abs(got - np.array(ref)) / np.maximum(np.abs(np.array(ref)), 1e-12)) <= 1e-9
     assert np.allclose(b._hyp.tau_beta, a._hyp.tau_beta, rtol=1e-10)
+
+
+@pytest.mark.parametrize("ld_dtype,blocks", [(np.int8, (300, 517, 64, 1200)), (np.float32, (257, 33)), (np.int8, (4600, 100))])
+def test_fused_sums_match_the_sums_kernel(vb, ld_dtype, blocks, monkeypatch):
+    """The reductions fused into the sweep's output role (viprs_b200_e_step_fused_f32, kernel version 2) against
+    viprs_b200_sums_f32 run on the arrays the same sweep left behind -- including a tiled LD block and two chromosome
+    segments."""
+    import torch
+    monkeypatch.setenv("VIPRS_B200_FAST", "2")
+    from viprs_b200 import _lib
+    from viprs_b200.ld import _stream_ptr
+    from viprs_b200.model import VIPRS
+    T = np.float32
+    rng = np.random.default_rng(12)
+    P = make_block_ld(rng, blocks, ld_dtype, T)
+    n = np.floor(rng.uniform(4e4, 6e4, P["M"]))
+    half = blocks[0]
+    ip = P["indptr"]
+    data = {1: dict(ld_data=P["data"][:ip[half]], ld_indptr=ip[:half + 1], ld_left_bound=P["lb"][:half], std_beta=P["beta"][:half],
+                    n_per_snp=n[:half]),
+            2: dict(ld_data=P["data"][ip[half]:], ld_indptr=ip[half:] - ip[half], ld_left_bound=P["lb"][half:] - half,
+                    std_beta=P["beta"][half:], n_per_snp=n[half:])}
+    m = VIPRS(data=data, float_precision="float32")
+    m.initialize({"pi": 0.02, "sigma_epsilon": 0.8})
+    for it in range(3):
+        m.e_step()
+        assert m._sums_fused
+        fused = m._sums_dev.clone()
+        L = _lib.lib()
+        ref = torch.zeros_like(fused)
+        rc = L.viprs_b200_sums_f32(m.M, 1, 0, 2, m._seg_dev.data_ptr(), m._g.data_ptr(), m._mu.data_ptr(), m._eta.data_ptr(),
+                                   m._q.data_ptr(), m._diff.data_ptr(), m.std_beta_dev.data_ptr(), m.n_per_snp_dev.data_ptr(),
+                                   m._theta_dev.data_ptr(), None, 2.0, m._ws.data_ptr(), m._ws.numel(), ref.data_ptr(), _stream_ptr())
+        assert rc == 0
+        torch.cuda.synchronize()
+        a, b = fused.cpu().numpy(), ref.cpu().numpy()
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) <= 1e-11, (it, a, b)
+        m.m_step()
+
+
+@pytest.mark.parametrize("tn,un,blocks", [("f32", "i8", (257, 64, 1, 2, 33, 700, 17)), ("f32", "i16", (4096, 500)),
+                                          ("f32", "f32", (6200,)), ("f32", "i8", (4096,))])
+def test_kernel_version_2_matches_oracle(vb, oracle_built, tn, un, blocks, monkeypatch):
+    """The alternative chain / output-warp organisation of the register-resident kernel (VIPRS_B200_FAST=2)."""
+    monkeypatch.setenv("VIPRS_B200_FAST", "2")
+    T = np.float32
+    U = {"i8": np.int8, "i16": np.int16, "f32": np.float32}[un]
+    rng = np.random.default_rng(1000 + len(blocks))
+    P = make_block_ld(rng, blocks, U, T)
+    hy = _hyper(rng, P["M"], T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= 1e-4, (k, relmax(got[k], ref[k]))

@@ -61,6 +61,7 @@ SIGNATURES = {
     "viprs_b200_sums_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "viprs_b200_sums_f32": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 10 + [_f64, _vp, _i64, _vp, _vp]),
     "viprs_b200_sums_f64": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 10 + [_f64, _vp, _i64, _vp, _vp]),
+    "viprs_b200_e_step_fused_f32": (ctypes.c_int, [_vp] * 10 + [_f32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "viprs_b200_em_update": (ctypes.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "viprs_b200_cpp_e_step_grid": (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32] + [_vp] * 9 + [_f64, _i32, _i32]),
 }

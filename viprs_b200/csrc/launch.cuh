@@ -74,17 +74,20 @@ static int launch_fast_ver(const viprs_b200_ld* ld, SweepPlan p, const typename 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
-        kern<<<p.n_blocks, FAST_WARPS * WARP, FL.total, st>>>(pp, FL, ma, sa);
+        kern<<<p.n_blocks, fast_threads<VER>(), FL.total, st>>>(pp, FL, ma, sa);
     });
 }
 
-// VIPRS_B200_FAST = 1: the round-1 chain (window gathered per step, outputs written by the chain warp); 2 (default):
-// constant-stride window layout, outputs written by the producer warp
+// VIPRS_B200_FAST = 1 (default): chain warp gathers its window coefficients per step and writes the outputs itself.
+// 2: constant-stride window layout, two accumulators per chain lane switched at 32-row boundaries, an 11th warp writes
+// the outputs and can accumulate the M-step / ELBO sums (viprs_b200_e_step_fused_f32).  Measured on the C2 workload
+// (B200, profiles/r02_c2_fast_versions.txt): the chain's share of a panel drops from ~2,600 to ~1,400 cycles, but the
+// sweep is bound by the A / C warps, not by the chain -- 1.021 ms (1) vs 1.053 ms (2), 1.19 ms with the fused sums.
 template <typename U, typename Model, int NLIMB>
 static int launch_fast_one(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
                            const StateArgs<float>& sa, cudaStream_t st) {
-    if (env_int("VIPRS_B200_FAST", 2) == 1) return launch_fast_ver<U, Model, NLIMB, 1>(ld, p, ma, sa, st);
-    return launch_fast_ver<U, Model, NLIMB, 2>(ld, p, ma, sa, st);
+    if (env_int("VIPRS_B200_FAST", 1) == 2) return launch_fast_ver<U, Model, NLIMB, 2>(ld, p, ma, sa, st);
+    return launch_fast_ver<U, Model, NLIMB, 1>(ld, p, ma, sa, st);
 }
 
 template <typename T, typename U, typename Model>
@@ -237,6 +240,43 @@ static int e_step_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_ga
         if (rc == 0 && materialize_q) rc = launch_backward<T, U>(ld, eta, q, dq, st);
         return rc;
     });
+}
+
+// Sweep with the M-step / ELBO reductions fused into its output role (register-resident kernel version 2, float32
+// state, spike-and-slab, no q offset): one launch per phase writes every unit's partial sums, a one-warp-per-slot
+// kernel folds them per chromosome segment into sums[nseg][VIPRS_B200_NSUMS].  VIPRS_B200_EUNSUPPORTED when the
+// configuration is not covered (callers then run the sweep and viprs_b200_sums_* separately).
+template <typename T>
+static int e_step_fused_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
+                                 T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq,
+                                 const double* n_per_snp, const double* theta, int nseg, const int32_t* seg_ptr,
+                                 double* sums, cudaStream_t st) {
+    if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult ||
+        !n_per_snp || !theta || !seg_ptr || !sums || nseg <= 0)
+        return VIPRS_B200_EINVAL;
+    if constexpr (sizeof(T) != 4) {
+        return VIPRS_B200_EUNSUPPORTED;
+    } else {
+        if (env_int("VIPRS_B200_FAST", 1) != 2 || env_int("VIPRS_B200_FUSED_SUMS", 1) == 0) return VIPRS_B200_EUNSUPPORTED;
+        typename SlabModel<T>::Args ma{std_beta, u_logs, shvt, mu_mult, var_gamma, var_mu, dq};
+        StateArgs<T> sa{eta, q, eta_diff};
+        sa.n_per_snp = n_per_snp; sa.theta = reinterpret_cast<const Theta*>(theta);
+        sa.unit_partial = reinterpret_cast<double*>(ld->d_unit_partial);
+        return for_ld_dtype<T>(ld, [&](auto tag) {
+            using U = decltype(tag);
+            if constexpr (sizeof(U) == 8) {
+                return (int)VIPRS_B200_EUNSUPPORTED;
+            } else {
+                if (!fast_path_ok<T, U, SlabModel<T>>(ld)) return (int)VIPRS_B200_EUNSUPPORTED;
+                int rc = launch_sweep<T, U, SlabModel<T>>(ld, ma, sa, nullptr, dq, st);
+                if (rc) return rc;
+                reduce_units_kernel<T><<<nseg, WARP * NS, 0, st>>>(ld->n_blocks, ld->d_blk_row, seg_ptr,
+                                                                   reinterpret_cast<const double*>(ld->d_unit_partial), sums);
+                const cudaError_t e = cudaGetLastError();
+                return e == cudaSuccess ? (int)VIPRS_B200_OK : (int)e;
+            }
+        });
+    }
 }
 
 template <typename T>

@@ -392,6 +392,8 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMalloc(&h->d_panel_need, sizeof(int32_t) * std::max(np, 1)));
         CUDA_TRY(cudaMalloc(&h->d_blk_order, sizeof(int32_t) * nb));
         CUDA_TRY(cudaMalloc(&h->d_items_diag, sizeof(int4) * nb));
+        CUDA_TRY(cudaMalloc(&h->d_unit_partial, sizeof(double) * VIPRS_B200_NSUMS * (size_t)nb));
+        CUDA_TRY(cudaMemsetAsync(h->d_unit_partial, 0, sizeof(double) * VIPRS_B200_NSUMS * (size_t)nb, stream));
         CUDA_TRY(cudaMalloc(&h->d_items_bwd, sizeof(int4) * std::max<size_t>(items_bwd.size(), 1)));
         CUDA_TRY(cudaMalloc(&h->d_items_bwd_ext, sizeof(int4) * std::max<size_t>(items_bwd_ext.size(), 1)));
         CUDA_TRY(cudaMemcpyAsync(h->d_items_bwd, items_bwd.data(), sizeof(int4) * items_bwd.size(), cudaMemcpyHostToDevice, stream));
@@ -530,7 +532,7 @@ extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     if (!h) return VIPRS_B200_OK;
     cudaFree(h->d_dense); cudaFree(h->d_dblk_off);
     cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext); cudaFree(h->d_items_bwd); cudaFree(h->d_items_bwd_ext);
-    cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws);
+    cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws); cudaFree(h->d_unit_partial);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
     cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);
     delete h;

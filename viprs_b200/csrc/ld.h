@@ -55,6 +55,7 @@ struct viprs_b200_ld {
     int32_t n_items_bwd = 0, n_items_bwd_ext = 0;
     std::vector<int32_t> h_ext_phase_ptr;   // [n_phases+1] slice of d_items_ext belonging to phase p
     std::vector<int32_t> h_items_cols;      // max columns of an item per phase / overall (grid sizing)
+    void* d_unit_partial = nullptr;   // [n_blocks][VIPRS_B200_NSUMS] doubles: per-unit sums of the fused sweep
     mutable void* d_host_ws = nullptr;   // staging of HOST state arrays (viprs_b200_cpp_e_step_resident), grown on demand
     mutable int64_t host_ws_bytes = 0;
     mutable void* d_fext = nullptr;   // [M] scratch of the state type (8 bytes per row): forward-external accumulator

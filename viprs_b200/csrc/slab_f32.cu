@@ -18,3 +18,12 @@ extern "C" int viprs_b200_q_offset_f32(const viprs_b200_ld_t* ld, const float* e
                                       float* q_offset_out, void* stream) {
     return vb::q_offset_dispatch<float>(ld, eta, q, dq_scale, q_offset_out, (cudaStream_t)stream);
 }
+
+extern "C" int viprs_b200_e_step_fused_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma, float* var_mu,
+                                           float* eta, float* q, float* eta_diff, const float* u_logs,
+                                           const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
+                                           const double* n_per_snp, const double* theta, int32_t nseg,
+                                           const int32_t* seg_ptr, double* sums, void* stream) {
+    return vb::e_step_fused_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau,
+                                            mu_mult, dq_scale, n_per_snp, theta, nseg, seg_ptr, sums, (cudaStream_t)stream);
+}

@@ -33,6 +33,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "em_math.cuh"
 
 namespace vb {
 
@@ -104,6 +105,7 @@ struct SlabModel {
     };
     static constexpr bool kHeavy = false;
     static constexpr bool kDualGroups = true;      // chain: separate branch-free code for full 4-step groups
+    static constexpr bool kFusedSums = true;       // the output role can accumulate the M-step / ELBO sums (layout 0)
     struct Raw { T beta, mm, sv, ul; };
     struct Lane { T c0, c1, a0, a1, ul; };      // mu = c1 X + c0 ;  sqrt(tau/2) mu = a1 X + a0
     struct Out { T mu, g; };
@@ -149,6 +151,7 @@ struct MixModel {
         const T* std_beta; const T* u_logs; const T* sqrt_half_var_tau; const T* mu_mult; const T* log_null_pi;
         T* var_gamma; T* var_mu; T dq; int K;
     };
+    static constexpr bool kFusedSums = false;        // (M,K) sums stay in the streaming kernel
     static constexpr bool kHeavy = (KMAX > 4);       // register-hungry: always one CTA per SM
     static constexpr bool kDualGroups = false;       // the step is large: a second inlined copy costs more (instruction
                                                      // cache) than its per-step branches (measured on the C4 workload)
@@ -226,7 +229,13 @@ template <> __device__ __forceinline__ double eps_of<double>() { return 1e-8; } 
 //   bext: backward-type terms of a tiled block (sum_{k in later tiles} R_jk eta_k(old)); like the in-tile backward dots
 //         they are NOT part of the forward q.
 template <typename T>
-struct StateArgs { T* eta; T* q; T* eta_diff; const T* fext = nullptr; const T* bext = nullptr; T fscale = T(1); };
+struct StateArgs {
+    T* eta; T* q; T* eta_diff; const T* fext = nullptr; const T* bext = nullptr; T fscale = T(1);
+    // fused M-step / ELBO reductions (register-resident kernel, version 2, spike-and-slab): when unit_partial != nullptr
+    // the output role also accumulates the VIPRS_B200_S_* sums of its sweep unit (float64, fixed order) and writes them
+    // to unit_partial[unit][VIPRS_B200_NSUMS]; reduce_units_kernel folds them per chromosome afterwards
+    const double* n_per_snp = nullptr; const Theta* theta = nullptr; double* unit_partial = nullptr;
+};
 
 template <typename T> __device__ __forceinline__ void load_state_vec(const T* src, T* dst, int n16) {
     const uint4* sp = reinterpret_cast<const uint4*>(src);
@@ -807,125 +816,126 @@ __device__ __forceinline__ void chain_role2(const SweepPlan& p, const typename M
     }
 }
 
-// Producer + output role of version 2: issues the TMA panels like producer_role and, while it would otherwise wait
-// for a free stage, writes the outputs of the panels the chain has finished: the update of every row is re-evaluated
-// from the X the chain saved (same function, same inputs: same bits) and var_mu / var_gamma / eta / eta_diff / q go to
-// global memory from here, off the chain's serial path.
-template <typename T, typename U, typename Model>
-__device__ __forceinline__ void producer_out_role(const SweepPlan& p, const typename Model::Args& ma,
-                                                  const StateArgs<T>& sa, unsigned char* smem, int4* rowmeta,
-                                                  int4* panelmeta, uint64_t* full, uint64_t* empty, const OutRings& orr,
-                                                  int r0, int B, int pan0, int NP, int lane, int* rowbase,
-                                                  int4* panelmeta2) {
-    constexpr int EPV = LdTraits<U>::EPV;
-    constexpr int ES = (int)sizeof(U);
-    const int NST = p.nst;
-    const unsigned char* gsrc = p.packed;
+// Output role of version 2 (its own warp): writes the outputs of the panels the chain has finished.  The update of every
+// row is re-evaluated from the X the chain saved (same function, same inputs: same bits) and var_mu / var_gamma / eta /
+// eta_diff / q go to global memory from here, off the chain's serial path.  With sa.unit_partial set it also accumulates
+// the M-step / ELBO sums of the sweep unit (the per-SNP terms of viprs_b200_sums_*, em.cu) from the values it writes.
+template <typename T, typename Model>
+__device__ __forceinline__ void output_role(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
+                                            const OutRings& orr, int r0, int pan0, int NP, int lane, int unit) {
     const T eps = eps_of<T>();
     const T dq = ma.dq;
-    // ---- output state: parameters of the next panel to write are prefetched one panel ahead ----
-    int out_u = 0;
-    typename Model::Raw oraw;
-    T oeo = T(0);
-    int ors = 0, ore = 0;
-    auto prefetch_out = [&]() {
-        if (out_u >= NP) return;
-        ors = p.panel_row[pan0 + out_u]; ore = p.panel_row[pan0 + out_u + 1];
-        const bool ok = lane < ore - ors;
-        Model::load_raw(ma, ors + lane, ok, oraw);
-        oeo = ok ? sa.eta[ors + lane] : T(0);
-    };
-    prefetch_out();
-    auto drain = [&]() {
-        while (out_u < NP && ld_acquire(orr.chain_panels) >= (uint32_t)(out_u + 1)) {
-            const int P = ore - ors;
-            if (lane < P) {
-                typename Model::Lane L;
-                Model::derive(ma, oraw, L);
-                const uint32_t slot = (uint32_t)((ors - r0 + lane) & (RR - 1)) * sizeof(T);
-                const T Xown = lds_t(orr.a_xown + slot, T());
-                const T bsum = lds_t(orr.a_bsum + slot, T());
-                T en, d;
-                bool skip;
-                typename Model::Out o;
-                Model::step(L, Xown, oeo, eps, en, d, skip, o);
-                const int row = ors + lane;
-                Model::store(ma, row, skip, o);
-                if (!skip) sa.eta[row] = en;                                       // :431
-                sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
-                sa.q[row] = dq * (Xown - bsum);                                    // forward part of q
-            }
-            __syncwarp();
-            if (lane == 0) st_release(orr.out_rows, (uint32_t)(ore - r0));
-            ++out_u;
-            prefetch_out();
-        }
-    };
-    (void)B;
-    int s = 0, k = 0;
-    for (int v = 0; v < NP; ++v) {
-        const int rs = p.panel_row[pan0 + v], re = p.panel_row[pan0 + v + 1];
-        const int P = re - rs;
-        const int64_t obase = p.prow[rs];
-        const int64_t oend = p.prow[re];
-        int64_t o0 = 0, o1 = 0;
-        int c = 0;
-        if (lane < P) { o0 = p.prow[rs + lane]; o1 = p.prow[rs + lane + 1]; c = p.pcs[rs + lane] - r0; }
-        const int need_next = (v + 1 < NP) ? p.panel_need[pan0 + v + 1] : 0;
-        int vs = 0x7fffffff, ve = 0;
-        int lo = 0, hi = 0x7fffffff;
-        int4 m = make_int4(0, 0, 0, 0);
-        if (lane < P) {
-            const int nv = (int)(o1 - o0) / EPV;
-            const int vs_r = c / EPV;
-            m.x = (int)p.L.stages + s * p.stage_bytes + (int)((o0 - obase) * ES) - vs_r * 16;
-            m.y = vs_r; m.z = vs_r + nv; m.w = need_next;
-            if (nv > 0) { vs = vs_r; ve = vs_r + nv; }
-            lo = vs_r; hi = vs_r + nv;
-        }
+    [[maybe_unused]] const bool fuse = Model::kFusedSums && sa.unit_partial != nullptr;
+    [[maybe_unused]] double acc[NS];
+    [[maybe_unused]] double on = 0.0, on_next = 0.0, nscale = 0.0, tau_b = 0.0;
+    if constexpr (Model::kFusedSums) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            vs = min(vs, __shfl_xor_sync(0xffffffffu, vs, o));
-            ve = max(ve, __shfl_xor_sync(0xffffffffu, ve, o));
-            lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = min(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        for (int i = 0; i < NS; ++i) acc[i] = 0.0;
+        if (fuse) { const Theta th = sa.theta[0]; nscale = (1.0 + th.lambda_min) / th.sigma_epsilon; tau_b = th.tau_beta; }
+    }
+    typename Model::Raw raw, raw_next;
+    T eo = T(0), eo_next = T(0);
+    int rs = 0, re = 0, rs_next = 0, re_next = 0;
+    auto prefetch = [&](int u) {                       // inputs of panel u (not yet rewritten: only this warp writes them)
+        if (u >= NP) return;
+        rs_next = p.panel_row[pan0 + u]; re_next = p.panel_row[pan0 + u + 1];
+        const bool ok = lane < re_next - rs_next;
+        Model::load_raw(ma, rs_next + lane, ok, raw_next);
+        eo_next = ok ? sa.eta[rs_next + lane] : T(0);
+        if constexpr (Model::kFusedSums) on_next = (fuse && ok) ? sa.n_per_snp[rs_next + lane] : 0.0;
+    };
+    prefetch(0);
+    for (int u = 0; u < NP; ++u) {
+        raw = raw_next; eo = eo_next; rs = rs_next; re = re_next; on = on_next;
+        prefetch(u + 1);
+        uint32_t spins = 0;
+        while (ld_acquire(orr.chain_panels) < (uint32_t)(u + 1)) {
+            __nanosleep(256);
+            if (++spins > kSpinLimit) __trap();
         }
-        const uint32_t bytes = (uint32_t)((oend - obase) * ES);
-        trace_ev(p, lane, 9, 0, v);
-        drain();
-        if (k > 0) {
-            uint32_t spins = 0;
-            while (!mbar_try_wait(&empty[s], (k - 1) & 1)) {     // the try_wait suspends for its time hint: a cheap idle loop
-                drain();
-                if (++spins > kSpinLimit) __trap();
+        if (lane < re - rs) {
+            typename Model::Lane L;
+            Model::derive(ma, raw, L);
+            const uint32_t slot = (uint32_t)((rs - r0 + lane) & (RR - 1)) * sizeof(T);
+            const T Xown = lds_t(orr.a_xown + slot, T());
+            const T bsum = lds_t(orr.a_bsum + slot, T());
+            T en, d;
+            bool skip;
+            typename Model::Out o;
+            Model::step(L, Xown, eo, eps, en, d, skip, o);
+            const int row = rs + lane;
+            Model::store(ma, row, skip, o);
+            if (!skip) sa.eta[row] = en;                                       // :431
+            sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
+            const T qf = dq * (Xown - bsum);
+            sa.q[row] = qf;                                                    // forward part of q
+            if constexpr (Model::kFusedSums) {
+                if (fuse) {
+                    // a skipped update leaves var_gamma / var_mu as they were (e_step.hpp:410-413): read them back
+                    const double g = skip ? (double)ma.var_gamma[row] : (double)o.g;
+                    const double mu = skip ? (double)ma.var_mu[row] : (double)o.mu;
+                    const double vt = on * nscale + tau_b;
+                    const double gc = clip_res(g), ivt = rcp_em<T>(vt), et = (double)en;
+                    const double ng = clip_res(1.0 - g);
+                    acc[VIPRS_B200_S_GAMMA] += g;
+                    acc[VIPRS_B200_S_GAMMA_MU2] += g * mu * mu;
+                    acc[VIPRS_B200_S_G_INV_TAU] += g * ivt;
+                    acc[VIPRS_B200_S_G_LOGG] += gc * log_unit<T>(gc);
+                    acc[VIPRS_B200_S_GCLIP] += gc;
+                    acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(vt);
+                    acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);
+                    acc[VIPRS_B200_S_ETA_Q] += 2.0 * et * (double)qf;          // eta'(R - I)eta = 2 sum eta_j F_j
+                    acc[VIPRS_B200_S_BETA_ETA] += (double)raw.beta * et;
+                    acc[VIPRS_B200_S_NG_LOGNG] += ng * log_one_minus<T>(g, ng);
+                    acc[VIPRS_B200_S_NGCLIP] += ng;
+                    acc[VIPRS_B200_S_ETA2] += et * et;
+                    acc[VIPRS_B200_S_MAX_DIFF] = fmax(acc[VIPRS_B200_S_MAX_DIFF], fabs(skip ? 0.0 : (double)d));
+                }
             }
-        }
-        trace_ev(p, lane, 9, 1, v);
-        if (lane < P) {
-            rowmeta[(rs - r0 + lane) & (RR - 1)] = m;
-            rowbase[(rs - r0 + lane) & (RR - 1)] = m.x;
-        }
-        if (lane == 0) {
-            panelmeta[s] = make_int4(P, ve > 0 ? vs : 0, ve, rs - r0);
-            panelmeta2[s] = make_int4(lo, hi, 0, 0);
         }
         __syncwarp();
-        if (lane == 0) {
-            if (bytes > 0) {
-                mbar_arrive_expect_tx(&full[s], bytes);
-                tma_load_1d(smem + p.L.stages + (size_t)s * p.stage_bytes, gsrc + obase * ES, bytes, &full[s]);
-            } else {
-                mbar_arrive(&full[s]);
+        if (lane == 0) st_release(orr.out_rows, (uint32_t)(re - r0));
+    }
+    if constexpr (Model::kFusedSums) {
+        if (fuse) {
+            // lanes by xor-shuffle (fixed order), one row of the unit table per sweep unit
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                double v = acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+                    v = (i == VIPRS_B200_S_MAX_DIFF) ? fmax(v, w) : v + w;
+                }
+                if (lane == 0) sa.unit_partial[(size_t)unit * NS + i] = v;
             }
-            trace_ev(p, lane, 9, 2, v);
         }
-        if (++s == NST) { s = 0; ++k; }
     }
-    uint32_t spins = 0;
-    while (out_u < NP) {
-        drain();
-        if (++spins > kSpinLimit) __trap();
+}
+
+// sums[seg][slot] = sum (max for MAX_DIFF) over the sweep units whose rows lie in chromosome segment seg, in unit order.
+// grid = nseg, block = 32 * NS threads is more than needed: one warp per slot, lanes stride the units.
+template <typename T>        // (a template only so that every translation unit may carry its own copy)
+__global__ void reduce_units_kernel(int n_units, const int32_t* __restrict__ unit_row, const int32_t* __restrict__ seg_ptr,
+                                    const double* __restrict__ unit_partial, double* __restrict__ sums) {
+    const int seg = blockIdx.x, slot = threadIdx.x / WARP, lane = threadIdx.x % WARP;
+    if (slot >= NS) return;
+    const int row0 = seg_ptr[seg], row1 = seg_ptr[seg + 1];
+    const bool is_max = slot == VIPRS_B200_S_MAX_DIFF;
+    double v = 0.0;
+    for (int u = lane; u < n_units; u += WARP) {
+        const int r = unit_row[u];
+        if (r >= row0 && r < row1) {
+            const double w = unit_partial[(size_t)u * NS + slot];
+            v = is_max ? fmax(v, w) : v + w;
+        }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, w) : v + w;
+    }
+    if (lane == 0) sums[(size_t)seg * NS + slot] = v;
 }
 
 // ---------------------------------------------------------------------------------------------

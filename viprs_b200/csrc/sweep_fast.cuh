@@ -93,8 +93,12 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // 
     return d;
 }
 
+// version 2 adds an output warp (warp FAST_WARPS): 11 warps per CTA, still two CTAs per SM (<= 88 registers)
+constexpr int FAST_OUTPUT_WARP = FAST_WARPS;
+template <int VER> constexpr int fast_threads() { return (VER == 2 ? FAST_WARPS + 1 : FAST_WARPS) * WARP; }
+
 template <typename U, typename Model, int NLIMB, int VER>
-__global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
+__global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
                                                                               const typename Model::Args ma,
                                                                               const StateArgs<float> sa) {
     using T = float;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
         if (lane == 0) red[warp] = mx;
         __syncthreads();
         mx = 0.f;
-        for (int w = 0; w < FAST_WARPS; ++w) mx = fmaxf(mx, red[w]);
+        for (int w = 0; w < (int)blockDim.x / WARP; ++w) mx = fmaxf(mx, red[w]);
         int ex = 0;
         if (mx > 0.f) frexpf(mx, &ex);                   // mx = m * 2^ex, m in [0.5, 1): block scale 2^ex > max |eta_old|
         const float qs = ldexpf(1.f, 7 * NLIMB - 1 - ex);        // eta -> fixed point Q, |Q| <= 2^(7 NLIMB - 1); exact scaling
@@ -225,13 +229,10 @@ __global__ void __launch_bounds__(FAST_WARPS * WARP, 2) sweep_fast_kernel(const 
     orr.a_xown = sbase + FL.xown; orr.a_bsum = sbase + FL.bsum;
     orr.chain_panels = sm.prog + NAW + NWW + NCW; orr.out_rows = sm.prog + NAW + NWW + NCW + 1;
     if (warp == FAST_PRODUCER_WARP) {
-        if constexpr (VER == 2)
-            producer_out_role<T, U, Model>(p, ma, sa, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, orr, r0, B, pan0, NP,
-                                           lane, reinterpret_cast<int*>(smem + FL.rowbase),
-                                           reinterpret_cast<int4*>(smem + FL.panelmeta2));
-        else
-            producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
-                             reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
+        producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
+                         reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
+    } else if (VER == 2 && warp == FAST_OUTPUT_WARP) {
+        if constexpr (VER == 2) output_role<T, Model>(p, ma, sa, orr, r0, pan0, NP, lane, blk);
     } else if (warp == FAST_CHAIN_WARP) {
         if constexpr (VER == 2) chain_role2<T, Model, NAW, NCW>(p, ma, sa, sm, orr, r0, B, pan0, NP, lane);
         else chain_role<T, Model, NAW, NCW, NWW>(p, ma, sa, sm, r0, B, pan0, NP, lane);

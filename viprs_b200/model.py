@@ -385,6 +385,25 @@ class VIPRS:
         _lib.check(rc, "viprs_b200_prepare")
 
     def _sweep(self):
+        self._sums_fused = False
+        if (self._qoff is None and self._tdt == torch.float32 and self._ncol == 1 and self._layout == 0
+                and getattr(self, "_fuse_ok", True)):
+            # the M-step / ELBO reductions ride along in the sweep's output role (viprs_b200_e_step_fused_f32)
+            L = _lib.lib()
+            rc = L.viprs_b200_e_step_fused_f32(self.ld.handle, self.std_beta_dev.data_ptr(), self._g.data_ptr(),
+                                               self._mu.data_ptr(), self._eta.data_ptr(), self._q.data_ptr(),
+                                               self._diff.data_ptr(), self._ul.data_ptr(), self._tt.data_ptr(),
+                                               self._mm.data_ptr(), float(self.dequantize_scale),
+                                               self.n_per_snp_dev.data_ptr(), self._theta_dev.data_ptr(),
+                                               len(self.chromosomes), self._seg_dev.data_ptr(), self._sums_dev.data_ptr(),
+                                               _stream_ptr())
+            if rc == 0:
+                self._q_is_forward = True
+                self._sums_fused = True
+                return
+            if rc != -6:                                   # -6: not covered by the fused kernel -> separate launches
+                _lib.check(rc, "viprs_b200_e_step_fused")
+            self._fuse_ok = False
         # with a q offset the sum eta'q cannot use the 2 x forward-part identity: materialise q every iteration
         e_step_device(self.ld, self.std_beta_dev, self._g, self._mu, self._eta, self._q, self._diff, self._ul, self._tt,
                       self._mm, self.dequantize_scale, self._qoff is not None, self._qoff)
@@ -403,7 +422,9 @@ class VIPRS:
         if self._sums is not None:
             return self._sums
         with torch.cuda.device(self.device):
-            if self.M > 0:
+            if self.M > 0 and getattr(self, "_sums_fused", False):
+                pass                                          # the sweep already left the table in _sums_dev
+            elif self.M > 0:
                 L = _lib.lib()
                 fn = L.viprs_b200_sums_f32 if self._tdt == torch.float32 else L.viprs_b200_sums_f64
                 tl = self._theta_logtau_dev()
@@ -476,13 +497,14 @@ class VIPRS:
         self._prepare(upload=False)
         if self.M > 0:
             self._sweep()
-            fn = L.viprs_b200_sums_f32 if self._tdt == torch.float32 else L.viprs_b200_sums_f64
-            rc = fn(self.M, self._ncol, self._layout, len(self.chromosomes), self._seg_dev.data_ptr(),
-                    self._g.data_ptr(), self._mu.data_ptr(), self._eta.data_ptr(), self._q.data_ptr(),
-                    self._diff.data_ptr(), self.std_beta_dev.data_ptr(), self.n_per_snp_dev.data_ptr(),
-                    self._theta_dev.data_ptr(), self._theta_logtau_dev(), 2.0 if self._q_is_forward else 1.0,
-                    self._ws.data_ptr(), self._ws.numel(), self._sums_dev.data_ptr(), _stream_ptr())
-            _lib.check(rc, "viprs_b200_sums")
+            if not getattr(self, "_sums_fused", False):
+                fn = L.viprs_b200_sums_f32 if self._tdt == torch.float32 else L.viprs_b200_sums_f64
+                rc = fn(self.M, self._ncol, self._layout, len(self.chromosomes), self._seg_dev.data_ptr(),
+                        self._g.data_ptr(), self._mu.data_ptr(), self._eta.data_ptr(), self._q.data_ptr(),
+                        self._diff.data_ptr(), self.std_beta_dev.data_ptr(), self.n_per_snp_dev.data_ptr(),
+                        self._theta_dev.data_ptr(), self._theta_logtau_dev(), 2.0 if self._q_is_forward else 1.0,
+                        self._ws.data_ptr(), self._ws.numel(), self._sums_dev.data_ptr(), _stream_ptr())
+                _lib.check(rc, "viprs_b200_sums")
         else:
             self._sums_dev.zero_()
         table = self._exchange.reduce_on_device(self._sums_dev)
@@ -796,6 +818,7 @@ class VIPRSMix(VIPRS):
         return f
 
     def _sweep(self):
+        self._sums_fused = False
         e_step_mixture_device(self.ld, self.std_beta_dev, self._g, self._mu, self._eta, self._q, self._diff, self._lnp,
                               self._ul, self._tt, self._mm, self.dequantize_scale, self._qoff is not None, self._qoff)
         self._q_is_forward = self._qoff is None
@@ -905,6 +928,7 @@ class VIPRSGrid(VIPRS):
     def _sweep(self):
         if not self._batched:
             return super()._sweep()
+        self._sums_fused = False
         key = tuple(self._active)
         if getattr(self, "_act_key", None) != key:                # (built outside any CUDA-graph capture)
             self._act_dev = torch.as_tensor(self._active, dtype=torch.int32, device=self.device)
