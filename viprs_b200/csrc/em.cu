@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
         acc[VIPRS_B200_S_G_INV_TAU] += g * ivt;
         acc[VIPRS_B200_S_G_LOGG] += gc * log_unit<T>(gc);                                   // VIPRS.py:562
         acc[VIPRS_B200_S_GCLIP] += gc;
-        acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(same_tau ? vt : n * nscale_l + tl.tau_beta);   // VIPRS.py:565 (log_var_tau cache)
+        acc[VIPRS_B200_S_G_LOG_TAU] += gc * log_tau<T>(same_tau ? vt : n * nscale_l + tl.tau_beta);   // VIPRS.py:565 (log_var_tau cache)
         acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);                          // VIPRS.py:571-573
         if (per_snp) {
             const size_t ev = layout == 0 ? e : (size_t)j;

@@ -37,6 +37,12 @@ struct LogNear {
         }
     }
 };
+// log(var_tau), var_tau ~ 1e4 .. 1e7 in float64.  float32 state: the float32 logarithm of the rounded value -- 1e-7
+// relative on a value of ~13, far inside what the float32 gamma next to it carries; float64 state: IEEE.
+template <typename T> __device__ __forceinline__ double log_tau(double vt) {
+    if constexpr (sizeof(T) == 4) return (double)logf((float)vt);
+    else return log(vt);
+}
 // log(x) for x = clip(g), g an exact value of type T in [0, 1]
 template <typename T> __device__ __forceinline__ double log_unit(double xc) {
     if constexpr (sizeof(T) == 4) return (double)logf((float)xc);

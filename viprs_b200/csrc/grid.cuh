@@ -205,32 +205,60 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         //   pbuf[2][5][GP][GT] of T : mu_mult, u_logs, half_var_tau, eta, std_beta of the lane's own rows
         //   wraw[GP][GWW] of U      : rows of the panel x columns [16u, 16u + 32)
         const uint32_t a_pbuf = sbase + p.L.pbuf, a_wraw = sbase + p.L.wraw;
+        // pbuf layout: [buffer u & 1][array 0..4][grid column g][panel row cl] -- the lane's own RPL rows of one array are
+        // RPL * sizeof(T) = 16 contiguous bytes, in shared memory and (column-major state) in global memory: one 16-byte
+        // cp.async and one 128-bit shared load per array when the column base is 16-byte aligned, scalar copies otherwise
+        auto pslot = [&](int u, int arr, int cl) {
+            return a_pbuf + (uint32_t)((((((u & 1) * 5) + arr) * GT + g) * GP + cl) * sizeof(T));
+        };
+        const bool vec_ok = ((colbase * sizeof(T)) % 16 == 0) && (((size_t)r0 * sizeof(T)) % 16 == 0) &&
+                            ((reinterpret_cast<size_t>(a.mu_mult) | reinterpret_cast<size_t>(a.u_logs) |
+                              reinterpret_cast<size_t>(a.half_var_tau) | reinterpret_cast<size_t>(a.eta) |
+                              reinterpret_cast<size_t>(a.std_beta) | reinterpret_cast<size_t>(a.var_mu) |
+                              reinterpret_cast<size_t>(a.var_gamma) | reinterpret_cast<size_t>(a.eta_diff)) % 16 == 0);
         auto stage_params = [&](int u) {
+            const int j = u * GP + RPL * w;
+            if (vec_ok && j + RPL <= B) {
+                const size_t idx = colbase + (size_t)j;
+                cp_async<16>(pslot(u, 0, RPL * w), a.mu_mult + idx);
+                cp_async<16>(pslot(u, 1, RPL * w), a.u_logs + idx);
+                cp_async<16>(pslot(u, 2, RPL * w), a.half_var_tau + idx);
+                cp_async<16>(pslot(u, 3, RPL * w), a.eta + idx);
+                cp_async<16>(pslot(u, 4, RPL * w), a.std_beta + r0 + j);
+                return;
+            }
 #pragma unroll
             for (int m = 0; m < RPL; ++m) {
-                const int cl = RPL * w + m, j = u * GP + cl;
-                if (j < B) {
-                    const size_t idx = colbase + (size_t)j;
-                    const uint32_t d = a_pbuf + (uint32_t)(((((u & 1) * 5) * GP + cl) * GT + g) * sizeof(T));
-                    cp_async<sizeof(T)>(d, a.mu_mult + idx);
-                    cp_async<sizeof(T)>(d + (uint32_t)(1 * GP * GT * sizeof(T)), a.u_logs + idx);
-                    cp_async<sizeof(T)>(d + (uint32_t)(2 * GP * GT * sizeof(T)), a.half_var_tau + idx);
-                    cp_async<sizeof(T)>(d + (uint32_t)(3 * GP * GT * sizeof(T)), a.eta + idx);
-                    cp_async<sizeof(T)>(d + (uint32_t)(4 * GP * GT * sizeof(T)), a.std_beta + r0 + j);
+                const int cl = RPL * w + m, jj = u * GP + cl;
+                if (jj < B) {
+                    const size_t idx = colbase + (size_t)jj;
+                    cp_async<sizeof(T)>(pslot(u, 0, cl), a.mu_mult + idx);
+                    cp_async<sizeof(T)>(pslot(u, 1, cl), a.u_logs + idx);
+                    cp_async<sizeof(T)>(pslot(u, 2, cl), a.half_var_tau + idx);
+                    cp_async<sizeof(T)>(pslot(u, 3, cl), a.eta + idx);
+                    cp_async<sizeof(T)>(pslot(u, 4, cl), a.std_beta + r0 + jj);
                 }
             }
         };
         auto fetch_params = [&](int u) {
+            T v[5][RPL];
+#pragma unroll
+            for (int arr = 0; arr < 5; ++arr) {
+                const uint4 q4 = lds128(pslot(u, arr, RPL * w));
+                memcpy(v[arr], &q4, 16);
+            }
 #pragma unroll
             for (int m = 0; m < RPL; ++m) {
-                const int cl = RPL * w + m;
-                const bool ok = u * GP + cl < B;
-                const uint32_t d = a_pbuf + (uint32_t)(((((u & 1) * 5) * GP + cl) * GT + g) * sizeof(T));
-                mm[m] = ok ? lds_t(d, T()) : T(0);
-                ul[m] = ok ? lds_t(d + (uint32_t)(1 * GP * GT * sizeof(T)), T()) : T(0);
-                hm[m] = ok ? mul_t(lds_t(d + (uint32_t)(2 * GP * GT * sizeof(T)), T()), mm[m]) : T(0);
-                eo[m] = ok ? lds_t(d + (uint32_t)(3 * GP * GT * sizeof(T)), T()) : T(0);
-                bt[m] = ok ? lds_t(d + (uint32_t)(4 * GP * GT * sizeof(T)), T()) : T(0);
+                const bool ok = u * GP + RPL * w + m < B;
+                mm[m] = ok ? v[0][m] : T(0);
+                ul[m] = ok ? v[1][m] : T(0);
+                hm[m] = ok ? mul_t(v[2][m], mm[m]) : T(0);
+                if constexpr (F32) {           // logit carried in base-2 units: the sigmoid's exponential is a bare MUFU.EX2
+                    hm[m] = mul_t(hm[m], T(1.4426950408889634));
+                    ul[m] = mul_t(ul[m], T(1.4426950408889634));
+                }
+                eo[m] = ok ? v[3][m] : T(0);
+                bt[m] = ok ? v[4][m] : T(0);
                 ndqeo[m] = -mul_t(dq, eo[m]);
             }
         };
@@ -316,7 +344,9 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                     // ndqeo = -dq*eta_old  =>  dq*eta_diff = fma(gamma, dq*mu, -dq*eta_old)
                     const T r = add_t(bt[m], -X[m]);
                     const T mu = mul_t(mm[m], r);                            // :613
-                    const T gam = sigmoid_t(fma_t(mul_t(hm[m], r), mu, ul[m]));   // :616-617
+                    T gam;                                                   // :616-617
+                    if constexpr (F32) gam = sigmoid2_t(fma_t(mul_t(hm[m], r), mu, ul[m]));
+                    else gam = sigmoid_t(fma_t(mul_t(hm[m], r), mu, ul[m]));
                     const T al = fma_t(gam, mul_t(dq, mu), ndqeo[m]);        // :620, :623
                     const T ab = shfl_t(al, src_lane);
 #pragma unroll
@@ -328,17 +358,34 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                     o_al[m] = own ? al : o_al[m];
                 }
             }
-            // panel outputs: every lane owns RPL rows of its grid column
+            // panel outputs: every lane owns RPL consecutive rows of its grid column (16 contiguous bytes per array)
+            T o_d[RPL], o_en[RPL];
 #pragma unroll
             for (int m = 0; m < RPL; ++m) {
                 const int cl = RPL * w + m;
                 const T av = (gvalid && j0 + cl < B) ? o_al[m] : T(0);
                 sts_t(a_alpha + (uint32_t)((((u % GAR) * GP + cl) * GT + g) * sizeof(T)), av);
-                if (gvalid && j0 + cl < B) {
-                    const size_t idx = colbase + (size_t)(j0 + cl);
-                    const T d = fma_t(o_g[m], o_mu[m], -eo[m]);               // :620
-                    a.var_mu[idx] = o_mu[m]; a.var_gamma[idx] = o_g[m]; a.eta_diff[idx] = d;
-                    a.eta[idx] = add_t(eo[m], d);                             // :633
+                o_d[m] = fma_t(o_g[m], o_mu[m], -eo[m]);                         // :620
+                o_en[m] = add_t(eo[m], o_d[m]);                                   // :633
+            }
+            if (gvalid) {
+                const int jr = j0 + RPL * w;
+                if (vec_ok && jr + RPL <= B) {
+                    const size_t idx = colbase + (size_t)jr;
+                    uint4 t4;
+                    memcpy(&t4, o_mu, 16); *reinterpret_cast<uint4*>(a.var_mu + idx) = t4;
+                    memcpy(&t4, o_g, 16); *reinterpret_cast<uint4*>(a.var_gamma + idx) = t4;
+                    memcpy(&t4, o_d, 16); *reinterpret_cast<uint4*>(a.eta_diff + idx) = t4;
+                    memcpy(&t4, o_en, 16); *reinterpret_cast<uint4*>(a.eta + idx) = t4;
+                } else {
+#pragma unroll
+                    for (int m = 0; m < RPL; ++m) {
+                        if (jr + m < B) {
+                            const size_t idx = colbase + (size_t)(jr + m);
+                            a.var_mu[idx] = o_mu[m]; a.var_gamma[idx] = o_g[m]; a.eta_diff[idx] = o_d[m];
+                            a.eta[idx] = o_en[m];
+                        }
+                    }
                 }
             }
             __syncwarp();

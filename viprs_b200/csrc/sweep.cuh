@@ -882,7 +882,7 @@ __device__ __forceinline__ void output_role(const SweepPlan& p, const typename M
                     acc[VIPRS_B200_S_G_INV_TAU] += g * ivt;
                     acc[VIPRS_B200_S_G_LOGG] += gc * log_unit<T>(gc);
                     acc[VIPRS_B200_S_GCLIP] += gc;
-                    acc[VIPRS_B200_S_G_LOG_TAU] += gc * log(vt);
+                    acc[VIPRS_B200_S_G_LOG_TAU] += gc * log_tau<T>(vt);
                     acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);
                     acc[VIPRS_B200_S_ETA_Q] += 2.0 * et * (double)qf;          // eta'(R - I)eta = 2 sum eta_j F_j
                     acc[VIPRS_B200_S_BETA_ETA] += (double)raw.beta * et;
