@@ -427,3 +427,68 @@ def test_kernel_version_2_matches_oracle(vb, oracle_built, tn, un, blocks, monke
     got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
     for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
         assert relmax(got[k], ref[k]) <= 1e-4, (k, relmax(got[k], ref[k]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# grid post-processing on the device (grid_utils.select_best_model / bayesian_model_average, pseudo-validation)
+# ---------------------------------------------------------------------------------------------------------
+def _fitted_grid(pathwise=False):
+    from viprs_b200.model import VIPRSGrid
+    data = _small_data(seed=8)
+    grid = [{"pi": p, "sigma_epsilon": s} for s in (0.7, 0.9) for p in (0.005, 0.02, 0.1)]
+    m = VIPRSGrid(data=data, grid=grid, float_precision="float32")
+    m.fit(pathwise=pathwise, max_iter=6, min_iter=20, f_abs_tol=0., x_abs_tol=0.)
+    return m, data, grid
+
+
+@pytest.mark.parametrize("pathwise", [False, True])
+def test_select_best_model_and_pseudo_validation(vb, pathwise):
+    import torch
+    m, data, grid = _fitted_grid(pathwise)
+    G = len(grid)
+    g = {c: m.var_gamma[c].cpu().numpy().astype(np.float64) for c in data}
+    mu = {c: m.var_mu[c].cpu().numpy().astype(np.float64) for c in data}
+    q = {c: m.q[c].cpu().numpy().astype(np.float64) for c in data}
+    elbos = np.asarray(m._elbo_final).copy()
+    rng = np.random.default_rng(0)
+    vbeta = {c: np.asarray(data[c]["std_beta"], dtype=np.float64) + rng.standard_normal(len(data[c]["std_beta"])) / 300 for c in data}
+    eta = np.concatenate([g[c] * mu[c] for c in data])
+    qq = np.concatenate([q[c] for c in data])
+    vb_all = np.concatenate([vbeta[c] for c in data])
+    want = (eta * vb_all[:, None]).sum(0) ** 2 / (eta * (qq + eta)).sum(0)          # eval/pseudo_metrics.py:149-152
+    got = m.pseudo_validate(vbeta)
+    assert got.shape == (G,) and np.allclose(got, want, rtol=1e-6)
+    best = int(np.argmax(want))
+    m.select_best_model("pseudo_validation", vbeta)
+    assert m.best_model_idx == best and m.n_models == 1
+    for c in data:
+        assert np.allclose(m.pip[c], g[c][:, best], rtol=1e-6) and np.allclose(m.post_mean_beta[c], (g[c] * mu[c])[:, best], rtol=1e-5)
+    assert abs(m.pi - grid[best]["pi"]) < 1e-7 and abs(m.sigma_epsilon - grid[best]["sigma_epsilon"]) < 1e-6
+    m2, _, _ = _fitted_grid(pathwise)
+    m2.select_best_model("ELBO")
+    assert m2.best_model_idx == int(np.argmax(elbos))
+
+
+def test_bayesian_model_average(vb):
+    m, data, grid = _fitted_grid(False)
+    elbos = np.asarray(m._elbo_final).copy()
+    w = np.exp(elbos - elbos.max()); w /= w.sum()                                  # scipy.special.softmax
+    g = {c: m.var_gamma[c].cpu().numpy().astype(np.float64) for c in data}
+    mu = {c: m.var_mu[c].cpu().numpy().astype(np.float64) for c in data}
+    q = {c: m.q[c].cpu().numpy().astype(np.float64) for c in data}
+    vt = {c: m.var_tau[c].cpu().numpy() for c in data}
+    M = sum(len(data[c]["std_beta"]) for c in data)
+    m.bayesian_model_average()
+    ga = {c: (g[c] * w).sum(1) for c in data}
+    mua = {c: (mu[c] * w).sum(1) for c in data}
+    qa = {c: (q[c] * w).sum(1) for c in data}
+    vta = {c: (vt[c] * w).sum(1) for c in data}
+    zeta = {c: ga[c].astype(np.float32).astype(np.float64) * (mua[c].astype(np.float32).astype(np.float64) ** 2 + 1. / vta[c]) for c in data}
+    for c in data:
+        assert np.allclose(m.pip[c], ga[c], rtol=2e-6)
+        assert np.allclose(m.post_mean_beta[c], ga[c] * mua[c], rtol=1e-5, atol=1e-12)
+    pi = np.mean([ga[c].mean() for c in data])                                      # VIPRS.py:434 on the averaged state
+    tau = pi * M / sum(zeta[c].sum() for c in data)
+    assert abs(m.pi - pi) <= 1e-6 * pi and abs(m.tau_beta - tau) <= 1e-5 * tau and m.n_models == 1
+    sg = sum((zeta[c] + qa[c] * (ga[c] * mua[c])).sum() for c in data)
+    assert abs(m._sigma_g - sg) <= 1e-4 * abs(sg)

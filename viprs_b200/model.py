@@ -329,6 +329,9 @@ class VIPRS:
         return float(self._hyp.sigma_g[0])
 
     def _var_tau_full(self, theta):
+        ov = getattr(self, "_var_tau_override", None)     # set by grid_post.bayesian_model_average (averaged var_tau)
+        if ov is not None:
+            return ov
         th = torch.as_tensor(theta, dtype=torch.float64, device=self.device)          # (ncol, 4)
         n = self.n_per_snp_dev
         vt = n[None, :] * ((1.0 + th[:, 3:4]) / th[:, 0:1]) + th[:, 1:2]              # (ncol, M)  VIPRS.py:400
@@ -1076,6 +1079,7 @@ class VIPRSGrid(VIPRS):
         self._sums = None
 
     def _finish_validation(self, elbos):
+        self._elbo_final = np.asarray(elbos, dtype=np.float64).copy()      # per-model final ELBO (model selection / BMA)
         msgs = [o.message for o in self.optim_results]
         try:
             vr = self.grid_table.copy()
@@ -1135,7 +1139,22 @@ class VIPRSGrid(VIPRS):
         self._finish_validation(elbos)
         return self
 
+    def select_best_model(self, criterion="ELBO", validation_std_beta=None):
+        """grid_utils.select_best_model (grid_utils.py:8-123) on the device-resident matrices; see grid_post.py."""
+        from . import grid_post
+        return grid_post.select_best_model(self, criterion, validation_std_beta)
+
+    def bayesian_model_average(self, normalization="softmax"):
+        """grid_utils.bayesian_model_average (grid_utils.py:126-193) on the device-resident matrices; see grid_post.py."""
+        from . import grid_post
+        return grid_post.bayesian_model_average(self, normalization)
+
+    def pseudo_validate(self, validation_std_beta):
+        from . import grid_post
+        return grid_post.pseudo_validate(self, validation_std_beta)
+
     def fit(self, pathwise=True, **fit_kwargs):
+        self._var_tau_override = None
         fit_kwargs.pop("disable_pbar", None)
         if pathwise:
             return self._fit_pathwise(**fit_kwargs)
