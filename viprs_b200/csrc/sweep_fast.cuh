@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
             [[maybe_unused]] int dig[DP4A ? NLIMB : 1];       // lane r: digit totals of row r of the panel
 #pragma unroll
             for (int l = 0; l < (DP4A ? NLIMB : 1); ++l) dig[l] = 0;
+#ifdef VB_WHATIF_SKIP_A
+            anyl = false;                    // timing experiment: no backward-dot arithmetic (results are wrong)
+#endif
             if (!anyl) {
                 if constexpr (!DP4A) {
                     if (lane < P) sm.partial[wa * RR + ((jl0 + lane) & (RR - 1))] = 0.f;
@@ -435,6 +438,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                 anyl |= live[c];
                 anyb |= live[c] && !inter[c];
             }
+#ifdef VB_WHATIF_SKIP_C
+            anyl = false;                    // timing experiment: no forward-axpy arithmetic (results are wrong)
+#endif
             if (anyl) {
 #pragma unroll kGroupUnroll
                 for (int rg = 0; rg < Pc; rg += 4) {
