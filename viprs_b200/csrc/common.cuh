@@ -74,6 +74,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > kSpinLimit) __trap();
     }
 }
+// the same on 32-bit shared-window addresses (no generic -> shared conversion in front of every barrier operation)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"((uint32_t)VB_TRYWAIT_NS)
+            : "memory");
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+    }
+}
 // 1-D TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -122,6 +141,14 @@ __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_a(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_a(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t target) {

@@ -19,8 +19,12 @@
 //   aux warp 0      producer : 1-D TMA bulk copies of (16 rows x <= 4 KB) stages into an nst-deep ring.
 //   aux warp 1      chain : lane = (grid column g, slot w).  Per 16-row panel it holds X[c,g] = published q + the
 //                      not-yet-published corrections of the previous and the current panel for the 16/NW columns it
-//                      owns, runs the scalar update of GT columns at once, broadcasts dq*eta_diff with one SHFL per
-//                      step, and keeps a decoded 16 x 32 window of LD coefficients in shared memory.
+//                      owns, runs the scalar update of GT columns at once and broadcasts dq*eta_diff with one SHFL per
+//                      step.  Nothing but the dependent path: operands and window coefficients arrive ready-made.
+//   aux warp 2      stager : stages the chain's operands (cp.async) in the form the steps consume and the decoded
+//                      16 x 32 window of LD coefficients up to GPB panels ahead, and writes the outputs of every finished
+//                      panel (measured on the C3 shape: the chain warp used to be busy 93 % of the time, 57 % of it in
+//                      this per-panel work, and the bulk warps waited for it 13 % of theirs).
 #pragma once
 #include <type_traits>
 
@@ -51,18 +55,21 @@ template <typename T> struct GridT;
 template <> struct GridT<float>  { static constexpr int GT = 8; };
 template <> struct GridT<double> { static constexpr int GT = 4; };
 
-struct GridLayout { uint32_t stages, wwin, wraw, pbuf, alpha, qpub, bars, prog, total; };
+constexpr int GPB = 3;            // depth (panels) of the parameter / window / output rings between the stager warp and the chain
+
+struct GridLayout { uint32_t stages, wwin, wraw, pbuf, obuf, alpha, qpub, bars, prog, total; };
 inline GridLayout make_grid_layout(int tsize, int gt, int stage_bytes, int nst) {
     GridLayout L;
     uint32_t o = 0;
     L.stages = o; o += (uint32_t)nst * (uint32_t)stage_bytes; o = (o + 127u) & ~127u;
-    L.wwin = o;   o += 2u * GP * GWW * (uint32_t)tsize;
+    L.wwin = o;   o += (uint32_t)GPB * GP * GWW * (uint32_t)tsize;
     L.wraw = o;   o += (uint32_t)GP * GWW * 8u;                       // raw window, sized for 8-byte LD elements
-    L.pbuf = o;   o += 2u * 5u * GP * (uint32_t)gt * (uint32_t)tsize;
+    L.pbuf = o;   o += (uint32_t)GPB * 6u * GP * (uint32_t)gt * (uint32_t)tsize;
+    L.obuf = o;   o += (uint32_t)GPB * 2u * GP * (uint32_t)gt * (uint32_t)tsize;
     L.alpha = o;  o += (uint32_t)GAR * GP * (uint32_t)gt * (uint32_t)tsize;
     L.qpub = o;   o += 2u * GP * (uint32_t)gt * (uint32_t)tsize;
     L.bars = o;   o += (2u * GNST_MAX + GAR) * 8u;
-    L.prog = o;   o += GRID_MAX_BW * 4u;
+    L.prog = o;   o += (GRID_MAX_BW + 1) * 4u;                        // bulk warps' panel counters + the stager's
     L.total = o;
     return L;
 }
@@ -153,11 +160,13 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
     uint32_t* prog = reinterpret_cast<uint32_t*>(smem + p.L.prog);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t a_alpha = sbase + p.L.alpha, a_qpub = sbase + p.L.qpub, a_wwin = sbase + p.L.wwin;
+    const uint32_t a_full = sbase + p.L.bars, a_empty = a_full + 8u * GNST_MAX, a_cdone = a_full + 16u * GNST_MAX;
+    const uint32_t a_prog = sbase + p.L.prog;
 
     if (tid == 0) {
         for (int s = 0; s < GNST_MAX; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)nbw); }
         for (int s = 0; s < GAR; ++s) mbar_init(&cdone[s], 1);
-        for (int w = 0; w < GRID_MAX_BW; ++w) prog[w] = 0;
+        for (int w = 0; w <= GRID_MAX_BW; ++w) prog[w] = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -166,6 +175,23 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
     // (each role's code must be dominated by its own setmaxnreg for ptxas to allocate against the new limit)
     if (warp >= aux0) {
       reg_dec<GRID_AUX_REGS>();
+      // lane = (grid column g, slot w) in the chain and in the stager: RPL consecutive rows of one grid column
+      const int g = lane % GT, w = lane / GT;
+      const int gi = tile * GT + g;
+      const bool gvalid = gi < p.n_active;
+      const size_t colbase = (size_t)p.active[gvalid ? gi : tile * GT] * M + (size_t)r0;
+      const uint32_t a_pbuf = sbase + p.L.pbuf, a_obuf = sbase + p.L.obuf;
+      uint32_t* pready = prog + GRID_MAX_BW;       // panels whose parameters and window the stager has made ready
+      // pbuf[GPB][6][GT][GP] of T: the chain's per-(SNP, column) operands, already in the form the steps consume
+      //   0 mu_mult | 1 u_logs (base-2 units in float32) | 2 half_var_tau * mu_mult (ditto) | 3 std_beta | 4 -dq * eta_old | 5 eta_old
+      // obuf[GPB][2][GT][GP] of T: var_mu, var_gamma of a finished panel (chain -> stager).
+      // A lane's RPL rows of one array are RPL * sizeof(T) = 16 contiguous bytes.
+      auto pslot = [&](int u, int arr) {
+          return a_pbuf + (uint32_t)(((((u % GPB) * 6 + arr) * GT + g) * GP + RPL * w) * sizeof(T));
+      };
+      auto oslot = [&](int u, int arr) {
+          return a_obuf + (uint32_t)(((((u % GPB) * 2 + arr) * GT + g) * GP + RPL * w) * sizeof(T));
+      };
       if (warp == aux0) {
         // =============================== producer ============================================
         int s = 0, k = 0;
@@ -189,127 +215,165 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 if (++s == NST) { s = 0; ++k; }
             }
         }
-      } else if (warp == aux0 + 1) {
-        // =============================== chain ===============================================
-        const int g = lane % GT, w = lane / GT;
-        const int gi = tile * GT + g;
-        const bool gvalid = gi < p.n_active;
-        const size_t colbase = (size_t)p.active[gvalid ? gi : tile * GT] * M + (size_t)r0;
+      } else if (warp == aux0 + 2) {
+        // =============================== stager ==============================================
+        // Everything of the per-SNP update that is not on the dependent path: it stages the chain's operands and the
+        // decoded LD window of a panel up to GPB panels ahead (cp.async, LDGSTS), and writes the outputs of every
+        // finished panel (e_step.hpp:613-620, 633) from the (var_mu, var_gamma) pairs the chain leaves in shared memory.
         const T dq = a.dq;
-        T mm[RPL], ul[RPL], hm[RPL], eo[RPL], bt[RPL], ndqeo[RPL];
-        T X[RPL], Y[RPL];
-#pragma unroll
-        for (int m = 0; m < RPL; ++m) { X[m] = T(0); Y[m] = T(0); }
-        // The per-(SNP, column) inputs of the next panel and the raw LD window of the next panel are staged through
-        // shared memory with cp.async (LDGSTS): no registers stay live across the panel.
-        //   pbuf[2][5][GP][GT] of T : mu_mult, u_logs, half_var_tau, eta, std_beta of the lane's own rows
-        //   wraw[GP][GWW] of U      : rows of the panel x columns [16u, 16u + 32)
-        const uint32_t a_pbuf = sbase + p.L.pbuf, a_wraw = sbase + p.L.wraw;
-        // pbuf layout: [buffer u & 1][array 0..4][grid column g][panel row cl] -- the lane's own RPL rows of one array are
-        // RPL * sizeof(T) = 16 contiguous bytes, in shared memory and (column-major state) in global memory: one 16-byte
-        // cp.async and one 128-bit shared load per array when the column base is 16-byte aligned, scalar copies otherwise
-        auto pslot = [&](int u, int arr, int cl) {
-            return a_pbuf + (uint32_t)((((((u & 1) * 5) + arr) * GT + g) * GP + cl) * sizeof(T));
-        };
+        const uint32_t a_wraw = sbase + p.L.wraw;
         const bool vec_ok = ((colbase * sizeof(T)) % 16 == 0) && (((size_t)r0 * sizeof(T)) % 16 == 0) &&
                             ((reinterpret_cast<size_t>(a.mu_mult) | reinterpret_cast<size_t>(a.u_logs) |
                               reinterpret_cast<size_t>(a.half_var_tau) | reinterpret_cast<size_t>(a.eta) |
                               reinterpret_cast<size_t>(a.std_beta) | reinterpret_cast<size_t>(a.var_mu) |
                               reinterpret_cast<size_t>(a.var_gamma) | reinterpret_cast<size_t>(a.eta_diff)) % 16 == 0);
-        auto stage_params = [&](int u) {
+        const int wr = lane >> 1, wh = lane & 1;       // window: lane stages / decodes row wr, half wh (16 elements)
+        auto stage = [&](int u) {
+            // ---- raw copies: mu_mult -> 0, u_logs -> 1, half_var_tau -> 2, std_beta -> 3, eta -> 5
             const int j = u * GP + RPL * w;
             if (vec_ok && j + RPL <= B) {
                 const size_t idx = colbase + (size_t)j;
-                cp_async<16>(pslot(u, 0, RPL * w), a.mu_mult + idx);
-                cp_async<16>(pslot(u, 1, RPL * w), a.u_logs + idx);
-                cp_async<16>(pslot(u, 2, RPL * w), a.half_var_tau + idx);
-                cp_async<16>(pslot(u, 3, RPL * w), a.eta + idx);
-                cp_async<16>(pslot(u, 4, RPL * w), a.std_beta + r0 + j);
-                return;
-            }
+                cp_async<16>(pslot(u, 0), a.mu_mult + idx);
+                cp_async<16>(pslot(u, 1), a.u_logs + idx);
+                cp_async<16>(pslot(u, 2), a.half_var_tau + idx);
+                cp_async<16>(pslot(u, 3), a.std_beta + r0 + j);
+                cp_async<16>(pslot(u, 5), a.eta + idx);
+            } else {
 #pragma unroll
-            for (int m = 0; m < RPL; ++m) {
-                const int cl = RPL * w + m, jj = u * GP + cl;
-                if (jj < B) {
-                    const size_t idx = colbase + (size_t)jj;
-                    cp_async<sizeof(T)>(pslot(u, 0, cl), a.mu_mult + idx);
-                    cp_async<sizeof(T)>(pslot(u, 1, cl), a.u_logs + idx);
-                    cp_async<sizeof(T)>(pslot(u, 2, cl), a.half_var_tau + idx);
-                    cp_async<sizeof(T)>(pslot(u, 3, cl), a.eta + idx);
-                    cp_async<sizeof(T)>(pslot(u, 4, cl), a.std_beta + r0 + jj);
+                for (int m = 0; m < RPL; ++m) {
+                    if (j + m < B) {
+                        const size_t idx = colbase + (size_t)(j + m);
+                        const uint32_t o = (uint32_t)(m * sizeof(T));
+                        cp_async<sizeof(T)>(pslot(u, 0) + o, a.mu_mult + idx);
+                        cp_async<sizeof(T)>(pslot(u, 1) + o, a.u_logs + idx);
+                        cp_async<sizeof(T)>(pslot(u, 2) + o, a.half_var_tau + idx);
+                        cp_async<sizeof(T)>(pslot(u, 3) + o, a.std_beta + r0 + j + m);
+                        cp_async<sizeof(T)>(pslot(u, 5) + o, a.eta + idx);
+                    }
                 }
             }
-        };
-        auto fetch_params = [&](int u) {
-            T v[5][RPL];
-#pragma unroll
-            for (int arr = 0; arr < 5; ++arr) {
-                const uint4 q4 = lds128(pslot(u, arr, RPL * w));
-                memcpy(v[arr], &q4, 16);
-            }
-#pragma unroll
-            for (int m = 0; m < RPL; ++m) {
-                const bool ok = u * GP + RPL * w + m < B;
-                mm[m] = ok ? v[0][m] : T(0);
-                ul[m] = ok ? v[1][m] : T(0);
-                hm[m] = ok ? mul_t(v[2][m], mm[m]) : T(0);
-                if constexpr (F32) {           // logit carried in base-2 units: the sigmoid's exponential is a bare MUFU.EX2
-                    hm[m] = mul_t(hm[m], T(1.4426950408889634));
-                    ul[m] = mul_t(ul[m], T(1.4426950408889634));
-                }
-                eo[m] = ok ? v[3][m] : T(0);
-                bt[m] = ok ? v[4][m] : T(0);
-                ndqeo[m] = -mul_t(dq, eo[m]);
-            }
-        };
-        // lane l stages / decodes row l/2, half l%2 (16 elements) of the window
-        const int wr = lane >> 1, wh = lane & 1;
-        auto stage_window = [&](int u) -> bool {
             const int row = u * GP + wr, col = u * GP + 16 * wh;
-            const bool ok = (row < B) && (col + 16 <= Bp);
-            if (ok) {
+            const bool wok = (row < B) && (col + 16 <= Bp);
+            if (wok) {
                 const unsigned char* src = gblk + (size_t)row * row_bytes + (size_t)col * ES;
 #pragma unroll
                 for (int c = 0; c < ES; ++c) cp_async<16>(a_wraw + (uint32_t)((wr * GWW + 16 * wh) * ES + 16 * c), src + 16 * c);
             }
-            return ok;
-        };
-        auto decode_window = [&](int u, bool ok) {
-            const uint32_t dst = a_wwin + (uint32_t)((((u & 1) * GP + wr) * GWW + 16 * wh) * sizeof(T));
+            cp_async_wait_all();
+            // ---- operands in the form the steps consume; rows past the block end and unused grid columns carry
+            // all-zero operands (their delta is exactly 0)
+            T v[6][RPL];
+#pragma unroll
+            for (int arr = 0; arr < 6; ++arr) {
+                if (arr == 4) continue;
+                const uint4 q4 = lds128(pslot(u, arr));
+                memcpy(v[arr], &q4, 16);
+            }
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                const bool ok = gvalid && (j + m < B);
+                const T mmv = ok ? v[0][m] : T(0);
+                T ulv = ok ? v[1][m] : T(0);
+                T hmv = ok ? mul_t(v[2][m], mmv) : T(0);
+                if constexpr (F32) {           // logit carried in base-2 units: the sigmoid's exponential is a bare MUFU.EX2
+                    hmv = mul_t(hmv, T(1.4426950408889634));
+                    ulv = mul_t(ulv, T(1.4426950408889634));
+                }
+                const T eov = ok ? v[5][m] : T(0);
+                v[0][m] = mmv; v[1][m] = ulv; v[2][m] = hmv;
+                v[3][m] = ok ? v[3][m] : T(0);
+                v[4][m] = -mul_t(dq, eov);
+                v[5][m] = eov;
+            }
+#pragma unroll
+            for (int arr = 0; arr < 6; ++arr) {
+                uint4 q4;
+                memcpy(&q4, v[arr], 16);
+                sts128(pslot(u, arr), q4);
+            }
+            // ---- decoded window
+            const uint32_t dst = a_wwin + (uint32_t)((((u % GPB) * GP + wr) * GWW + 16 * wh) * sizeof(T));
 #pragma unroll
             for (int c = 0; c < ES; ++c) {
-                T v[EPV];
-                if (ok) {
+                T x[EPV];
+                if (wok) {
                     const uint4 rv = lds128(a_wraw + (uint32_t)((wr * GWW + 16 * wh) * ES + 16 * c));
-                    GridDecode<T, U>::vec(rv, v);
+                    GridDecode<T, U>::vec(rv, x);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) v[e] = T(0);
+                    for (int e = 0; e < EPV; ++e) x[e] = T(0);
                 }
 #pragma unroll
-                for (int e = 0; e < EPV; ++e) sts_t(dst + (uint32_t)((c * EPV + e) * sizeof(T)), v[e]);
+                for (int e = 0; e < EPV; e += 16 / (int)sizeof(T)) {
+                    uint4 q4;
+                    memcpy(&q4, x + e, 16);
+                    sts128(dst + (uint32_t)((c * EPV + e) * sizeof(T)), q4);
+                }
             }
+            __syncwarp();
+            if (lane == 0) st_release(pready, (uint32_t)(u + 1));
         };
-
-        stage_params(0);
-        bool wok = stage_window(0);
-        cp_async_wait_all();
-        decode_window(0, wok);
-        fetch_params(0);
-        __syncwarp();
-
+        for (int u = 0; u < min(GPB, NP); ++u) stage(u);
+        for (int u = 0; u < NP; ++u) {
+            mbar_wait_a(a_cdone + 8u * (uint32_t)(u % GAR), (u / GAR) & 1);          // the chain has finished panel u
+            // panel outputs: every lane owns RPL consecutive rows of its grid column (16 contiguous bytes per array)
+            T o_mu[RPL], o_g[RPL], eo[RPL], o_d[RPL], o_en[RPL];
+            { uint4 q4 = lds128(oslot(u, 0)); memcpy(o_mu, &q4, 16);
+              q4 = lds128(oslot(u, 1)); memcpy(o_g, &q4, 16);
+              q4 = lds128(pslot(u, 5)); memcpy(eo, &q4, 16); }
+#pragma unroll
+            for (int m = 0; m < RPL; ++m) {
+                o_d[m] = fma_t(o_g[m], o_mu[m], -eo[m]);                         // :620
+                o_en[m] = add_t(eo[m], o_d[m]);                                   // :633
+            }
+            if (gvalid) {
+                const int jr = u * GP + RPL * w;
+                if (vec_ok && jr + RPL <= B) {
+                    const size_t idx = colbase + (size_t)jr;
+                    uint4 t4;
+                    memcpy(&t4, o_mu, 16); *reinterpret_cast<uint4*>(a.var_mu + idx) = t4;
+                    memcpy(&t4, o_g, 16); *reinterpret_cast<uint4*>(a.var_gamma + idx) = t4;
+                    memcpy(&t4, o_d, 16); *reinterpret_cast<uint4*>(a.eta_diff + idx) = t4;
+                    memcpy(&t4, o_en, 16); *reinterpret_cast<uint4*>(a.eta + idx) = t4;
+                } else {
+#pragma unroll
+                    for (int m = 0; m < RPL; ++m) {
+                        if (jr + m < B) {
+                            const size_t idx = colbase + (size_t)(jr + m);
+                            a.var_mu[idx] = o_mu[m]; a.var_gamma[idx] = o_g[m]; a.eta_diff[idx] = o_d[m];
+                            a.eta[idx] = o_en[m];
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                       // every lane has read its slots of ring entry u % GPB
+            if (u + GPB < NP) stage(u + GPB);
+        }
+      } else if (warp == aux0 + 1) {
+        // =============================== chain ===============================================
+        const T dq = a.dq;
+        T mm[RPL], ul[RPL], hm[RPL], bt[RPL], ndqeo[RPL];
+        T X[RPL], Y[RPL];
+#pragma unroll
+        for (int m = 0; m < RPL; ++m) { X[m] = T(0); Y[m] = T(0); }
         for (int u = 0; u < NP; ++u) {
             const int j0 = u * GP;
-            if (u + 1 < NP) { stage_params(u + 1); wok = stage_window(u + 1); }
-            // every bulk warp has applied (and published past) panel u-2
-            if (u >= 2) {
+            // the stager has made panel u ready; every bulk warp has applied (and published past) panel u-2
+            {
                 uint32_t spins = 0;
                 for (;;) {
-                    const bool ok = (lane >= nbw) || (ld_acquire(prog + lane) >= (uint32_t)(u - 1));
+                    bool ok = true;
+                    if (lane < nbw) ok = (u < 2) || (ld_acquire_a(a_prog + 4u * (uint32_t)lane) >= (uint32_t)(u - 1));
+                    else if (lane == GRID_MAX_BW) ok = ld_acquire_a(a_prog + 4u * GRID_MAX_BW) >= (uint32_t)(u + 1);
                     if (__all_sync(0xffffffffu, ok)) break;
                     if (++spins > kSpinLimit) __trap();
                 }
             }
+            { uint4 q4 = lds128(pslot(u, 0)); memcpy(mm, &q4, 16);
+              q4 = lds128(pslot(u, 1)); memcpy(ul, &q4, 16);
+              q4 = lds128(pslot(u, 2)); memcpy(hm, &q4, 16);
+              q4 = lds128(pslot(u, 3)); memcpy(bt, &q4, 16);
+              q4 = lds128(pslot(u, 4)); memcpy(ndqeo, &q4, 16); }
 #pragma unroll
             for (int m = 0; m < RPL; ++m) {
                 const int cl = RPL * w + m;
@@ -319,9 +383,9 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 X[m] = add_t(base, Y[m]);
                 Y[m] = T(0);
             }
-            const uint32_t wrow = a_wwin + (uint32_t)(((u & 1) * GP * GWW + RPL * w) * sizeof(T));
+            const uint32_t wrow = a_wwin + (uint32_t)(((u % GPB) * GP * GWW + RPL * w) * sizeof(T));
             // The steps below are branch-free and store-free: rows past the block end carry all-zero inputs (their
-            // delta is exactly 0), outputs are kept by predicated moves and written once per panel.
+            // delta is exactly 0), outputs are kept by predicated moves and handed over once per panel.
             T o_mu[RPL], o_g[RPL], o_al[RPL];
 #pragma unroll
             for (int m = 0; m < RPL; ++m) { o_mu[m] = T(0); o_g[m] = T(0); o_al[m] = T(0); }
@@ -358,44 +422,15 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                     o_al[m] = own ? al : o_al[m];
                 }
             }
-            // panel outputs: every lane owns RPL consecutive rows of its grid column (16 contiguous bytes per array)
-            T o_d[RPL], o_en[RPL];
+            // hand-over: scaled deltas to the bulk warps, (var_mu, var_gamma) to the stager
 #pragma unroll
-            for (int m = 0; m < RPL; ++m) {
-                const int cl = RPL * w + m;
-                const T av = (gvalid && j0 + cl < B) ? o_al[m] : T(0);
-                sts_t(a_alpha + (uint32_t)((((u % GAR) * GP + cl) * GT + g) * sizeof(T)), av);
-                o_d[m] = fma_t(o_g[m], o_mu[m], -eo[m]);                         // :620
-                o_en[m] = add_t(eo[m], o_d[m]);                                   // :633
-            }
-            if (gvalid) {
-                const int jr = j0 + RPL * w;
-                if (vec_ok && jr + RPL <= B) {
-                    const size_t idx = colbase + (size_t)jr;
-                    uint4 t4;
-                    memcpy(&t4, o_mu, 16); *reinterpret_cast<uint4*>(a.var_mu + idx) = t4;
-                    memcpy(&t4, o_g, 16); *reinterpret_cast<uint4*>(a.var_gamma + idx) = t4;
-                    memcpy(&t4, o_d, 16); *reinterpret_cast<uint4*>(a.eta_diff + idx) = t4;
-                    memcpy(&t4, o_en, 16); *reinterpret_cast<uint4*>(a.eta + idx) = t4;
-                } else {
-#pragma unroll
-                    for (int m = 0; m < RPL; ++m) {
-                        if (jr + m < B) {
-                            const size_t idx = colbase + (size_t)(jr + m);
-                            a.var_mu[idx] = o_mu[m]; a.var_gamma[idx] = o_g[m]; a.eta_diff[idx] = o_d[m];
-                            a.eta[idx] = o_en[m];
-                        }
-                    }
-                }
-            }
+            for (int m = 0; m < RPL; ++m)
+                sts_t(a_alpha + (uint32_t)((((u % GAR) * GP + RPL * w + m) * GT + g) * sizeof(T)), o_al[m]);
+            { uint4 t4;
+              memcpy(&t4, o_mu, 16); sts128(oslot(u, 0), t4);
+              memcpy(&t4, o_g, 16); sts128(oslot(u, 1), t4); }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cdone[u % GAR]);
-            if (u + 1 < NP) {
-                cp_async_wait_all();
-                decode_window(u + 1, wok);
-                fetch_params(u + 1);
-            }
-            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_cdone + 8u * (uint32_t)(u % GAR));
         }
       }
     } else {
@@ -450,18 +485,18 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         int s = 0, k = 0;
         for (int u = 0; u < NP; ++u) {
             const int nrows = min(GP, B - u * GP);
-            mbar_wait(&cdone[u % GAR], (u / GAR) & 1);
+            mbar_wait_a(a_cdone + 8u * (uint32_t)(u % GAR), (u / GAR) & 1);
             const uint32_t abase = a_alpha + (uint32_t)((u % GAR) * GP * GT * sizeof(T));
             for (int c = 0; c < nck; ++c) {
                 const int cb = min(GCW, row_bytes - c * GCW);
-                mbar_wait(&full[s], k & 1);
+                mbar_wait_a(a_full + 8u * (uint32_t)s, k & 1);
                 const uint32_t st = sbase + p.L.stages + (uint32_t)s * (uint32_t)p.stage_bytes;
                 bool any = false;
 #pragma unroll
                 for (int i = 0; i < NVT; ++i) any |= (vchunk[i] == c);
                 if (any) {
-                    // (a hand-pipelined variant that fetched row r+1's codes and deltas before row r's FMAs measured 1.5%
-                    // slower on B200: the second bulk warp of the sub-partition already covers the shared-memory latency)
+                    // (software-pipelined forms of this loop -- loads only, or loads + decode one row ahead in a two-row body --
+                    // measured slower on B200, as did decoding through I2F.S8 on the conversion unit: scripts/microbench/grid_loop_bench.cu)
 #pragma unroll 1
                     for (int r = 0; r < nrows; ++r) {
                         // the GT scaled deltas of row r: GT * sizeof(T) = 32 bytes, two broadcast loads
@@ -501,7 +536,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) mbar_arrive_a(a_empty + 8u * (uint32_t)s);
                 if (++s == NST) { s = 0; ++k; }
             }
             // publish the columns of panel u+2 (complete through panel u) for the chain
@@ -529,7 +564,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 }
             }
             __syncwarp();
-            if (lane == 0) st_release(&prog[warp], (uint32_t)(u + 1));
+            if (lane == 0) st_release_a(a_prog + 4u * (uint32_t)warp, (uint32_t)(u + 1));
         }
         // ---- epilogue: q back to global memory ------------------------------------------------
 #pragma unroll
