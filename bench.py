@@ -432,10 +432,10 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
         def e2e_step():
             if wl["model"] == "mix":
                 es.cpp_e_step_mixture_resident(model.ld, host["std_beta_dev"], host["_g"], host["_mu"], host["_eta"], host["_q"],
-                                               host["_diff"], host["_lnp"], host["_ul"], host["_tt"], host["_mm"], dq, True)
+                                               host["_diff"], host["_lnp"], host["_ul"], host["_tt"], host["_mm"], dq, False)
             else:
                 es.cpp_e_step_resident(model.ld, host["std_beta_dev"], host["_g"], host["_mu"], host["_eta"], host["_q"],
-                                       host["_diff"], host["_ul"], host["_tt"], host["_mm"], dq, True)
+                                       host["_diff"], host["_ul"], host["_tt"], host["_mm"], dq, False)
 
         e_steps = min(steps, 100)
         for _ in range(3):
@@ -456,8 +456,9 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
         out["e2e"] = {"value": M_all * G * e_steps / (ems * 1e-3), "unit": "SNP-updates/s",
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps,
                       "steps": e_steps,
-                      "call": "viprs_b200_cpp_e_step%s_resident (host state arrays of this rank's shard, q materialised, "
-                              "q_is_consistent=1)" % ("_mixture" if wl["model"] == "mix" else "")}
+                      "call": "viprs_b200_cpp_e_step%s_resident (host state arrays of this rank's shard; q in/out with the "
+                              "reference's incremental bookkeeping, nothing vouched: sweep + update_q_factor pass, in row chunks "
+                              "on internal streams so that copies and sweeps overlap)" % ("_mixture" if wl["model"] == "mix" else "")}
     del model
     torch.cuda.empty_cache()
     return out

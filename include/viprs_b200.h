@@ -179,6 +179,22 @@ int viprs_b200_backward_dot_f32(const viprs_b200_ld_t* ld, const float* x, float
 int viprs_b200_backward_dot_f64(const viprs_b200_ld_t* ld, const double* x, double* q,
                                 double dq_scale, void* stream);
 
+/* viprs_b200_e_step_incremental_f32 / viprs_b200_e_step_mixture_incremental_f32: cpp_e_step / cpp_e_step_mixture
+ * (e_step_cpp.pyx:91-105, 125-141) on DEVICE arrays with the reference's own bookkeeping of q -- q is in/out and
+ * maintained incrementally: inside the sweep q_j = q_in[j] + dq_scale * sum_{i<j} R_ij eta_diff_i (e_step.hpp:421),
+ * after it q[j] += dq_scale * sum_{k>j} R_jk eta_diff_k (update_q_factor, e_step.hpp:435-440).  Whatever the caller's q
+ * holds is honoured exactly as the reference does; the LD is read twice per call (like the reference), with no backward
+ * dots inside the sequential sweep.  float32 state, LD blocks <= 4096 SNPs, K <= 4; VIPRS_B200_EUNSUPPORTED otherwise
+ * (use viprs_b200_e_step_* with viprs_b200_q_offset_*). */
+int viprs_b200_e_step_incremental_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma, float* var_mu,
+                                      float* eta, float* q, float* eta_diff, const float* u_logs,
+                                      const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale, void* stream);
+int viprs_b200_e_step_mixture_incremental_f32(const viprs_b200_ld_t* ld, int32_t K, const float* std_beta, float* var_gamma,
+                                              float* var_mu, float* eta, float* q, float* eta_diff,
+                                              const float* log_null_pi, const float* u_logs,
+                                              const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
+                                              void* stream);
+
 /* ---- one-shot host-pointer drop-ins: exactly the reference's cpdef signatures -----------------
  * Same arrays, same in-place outputs as cpp_e_step(...) (e_step_cpp.pyx:91-122) with host (numpy)
  * buffers: upload, pack, sweep, materialise q, download.  `threads` is accepted and ignored
@@ -204,8 +220,11 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
  * host memory, as the reference does: per call the arrays cpp_e_step reads go host->device (std_beta, var_gamma, var_mu,
  * eta, q, u_logs, sqrt_half_var_tau, mu_mult), one sweep runs, q is materialised, and what cpp_e_step writes
  * (var_gamma, var_mu, eta, q, eta_diff) comes back; returns after the stream has drained.  Pinned host buffers make the
- * copies asynchronous.  q_is_consistent != 0: the caller vouches that q = dq (R - I) eta on entry (true on every
- * iteration of VIPRS.fit unless `param_0` was given) and the two extra LD passes of viprs_b200_q_offset_* are skipped. */
+ * copies asynchronous.  Where the incremental sweep applies (float32 state, LD blocks <= 4096 SNPs) the call runs
+ * viprs_b200_e_step_*incremental_f32 in row chunks on internal streams, so that the copies of one chunk overlap the sweep
+ * of another, and q_is_consistent is irrelevant.  Otherwise: q_is_consistent != 0: the caller vouches that
+ * q = dq (R - I) eta on entry (true on every iteration of VIPRS.fit unless `param_0` was given) and the two extra LD
+ * passes of viprs_b200_q_offset_* are skipped. */
 int viprs_b200_cpp_e_step_resident(const viprs_b200_ld_t* ld, int32_t float_dtype, const void* std_beta, void* var_gamma,
                                    void* var_mu, void* eta, void* q, void* eta_diff, const void* u_logs,
                                    const void* sqrt_half_var_tau, const void* mu_mult, double dq_scale,

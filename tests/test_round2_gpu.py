@@ -499,3 +499,111 @@ def test_bayesian_model_average(vb):
     assert abs(m.pi - pi) <= 1e-6 * pi and abs(m.tau_beta - tau) <= 1e-5 * tau and m.n_models == 1
     sg = sum((zeta[c] + qa[c] * (ga[c] * mua[c])).sum() for c in data)
     assert abs(m._sigma_g - sg) <= 1e-4 * abs(sg)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's incremental q on the device (viprs_b200_e_step_*incremental_f32) and the host-state round trip
+# that runs it in row chunks (viprs_b200_cpp_e_step*_resident)
+# ---------------------------------------------------------------------------------------------------------
+_INCR_BLOCKS = (700, 33, 257, 1, 2, 512, 300, 64, 129, 1000, 17, 400)      # 12 LD blocks -> 4 row chunks
+
+
+def _incr_start(rng0, M, T, q_in, K=0):
+    shape = (M, K) if K else (M,)
+    st = {"var_gamma": np.ascontiguousarray(rng0.uniform(0.01, 0.3 / max(K, 1), shape).astype(T)),
+          "var_mu": np.ascontiguousarray((0.01 * rng0.standard_normal(shape)).astype(T)), "eta_diff": np.zeros(M, T)}
+    eta = st["var_gamma"] * st["var_mu"]
+    st["eta"] = np.ascontiguousarray(eta.sum(axis=1) if K else eta).astype(T)
+    st["q"] = np.zeros(M, T) if q_in == "zero" else (0.003 * rng0.standard_normal(M)).astype(T)
+    return st
+
+
+@pytest.mark.parametrize("un", ["i8", "i16", "f32"])
+@pytest.mark.parametrize("q_in", ["zero", "garbage"])
+def test_incremental_sweep_matches_oracle(vb, oracle_built, un, q_in):
+    """cpp_e_step semantics with q in/out on device arrays: 3 sweeps from a warm start with an arbitrary q_in."""
+    import torch
+    T = np.float32
+    U = {"i8": np.int8, "i16": np.int16, "f32": np.float32}[un]
+    rng = np.random.default_rng(21)
+    P = make_block_ld(rng, _INCR_BLOCKS, U, T)
+    M = P["M"]
+    hy = _hyper(rng, M, T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 3, _incr_start(np.random.default_rng(9), M, T, q_in))
+    st = _incr_start(np.random.default_rng(9), M, T, q_in)
+    u_logs, shvt, mm, _ = hy
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    dev = {k: torch.from_numpy(v).cuda() for k, v in st.items()}
+    beta, ul, sv, m_ = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (P["beta"], u_logs, shvt, mm))
+    for _ in range(3):
+        vb.e_step_incremental_device(ld, beta, dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"],
+                                     ul, sv, m_, P["dq"])
+    torch.cuda.synchronize()
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(dev[k].cpu().numpy(), ref[k]) <= 1e-4, (k, relmax(dev[k].cpu().numpy(), ref[k]))
+    ld.destroy()
+
+
+def test_incremental_sweep_unsupported_for_float64(vb):
+    """float64 state is not covered by the incremental sweep: the entry says so, it does not compute something else."""
+    import torch
+    rng = np.random.default_rng(3)
+    P = make_block_ld(rng, (300, 120), np.float64, np.float64)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    z = torch.zeros(P["M"], dtype=torch.float32, device="cuda")
+    with pytest.raises(vb.ViprsB200Error) as ei:
+        vb.e_step_incremental_device(ld, z, z.clone(), z.clone(), z.clone(), z.clone(), z.clone(), z, z, z, 1.0)
+    assert ei.value.code == -6 or "unsupported" in str(ei.value).lower()
+    ld.destroy()
+
+
+@pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f32", "f32"), ("f64", "f64")])
+@pytest.mark.parametrize("q_in,vouch", [("zero", False), ("garbage", False)])
+def test_resident_host_state_matches_oracle(vb, oracle_built, tn, un, q_in, vouch):
+    """viprs_b200_cpp_e_step_resident: HOST state arrays on a resident LD, 3 calls.  float32: incremental sweep in row
+    chunks on internal streams; float64: q offset + one-pass sweep."""
+    T = np.float32 if tn == "f32" else np.float64
+    U = {"i8": np.int8, "f32": np.float32, "f64": np.float64}[un]
+    rng = np.random.default_rng(22)
+    P = make_block_ld(rng, _INCR_BLOCKS, U, T)
+    M = P["M"]
+    hy = _hyper(rng, M, T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 3, _incr_start(np.random.default_rng(9), M, T, q_in))
+    st = _incr_start(np.random.default_rng(9), M, T, q_in)
+    u_logs, shvt, mm, _ = hy
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    for _ in range(3):
+        vb.cpp_e_step_resident(ld, P["beta"], st["var_gamma"], st["var_mu"], st["eta"], st["q"], st["eta_diff"],
+                               np.ascontiguousarray(u_logs), np.ascontiguousarray(shvt), np.ascontiguousarray(mm), P["dq"], vouch)
+    tol = 1e-4 if T == np.float32 else 1e-10
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(st[k], ref[k]) <= tol, (k, relmax(st[k], ref[k]))
+    ld.destroy()
+
+
+@pytest.mark.parametrize("K", [1, 3, 4])
+def test_resident_mixture_host_state_matches_oracle(vb, oracle_built, K):
+    """viprs_b200_cpp_e_step_mixture_resident (int16 LD, float32): chunked incremental mixture sweep, 3 calls."""
+    T = np.float32
+    rng = np.random.default_rng(23)
+    P = make_block_ld(rng, _INCR_BLOCKS, np.int16, T)
+    M = P["M"]
+    n = np.floor(rng.uniform(4e4, 6e4, M))[:, None]
+    d = 2.0 ** np.linspace(-min(K - 1, 7), 0, K)
+    pis = 0.03 * np.ones(K) / K
+    tau = d * (M * np.dot(1. / d, pis) / 0.2)
+    vt = n / 0.8 + tau
+    u_logs = np.ascontiguousarray((np.log(pis) - np.log(1 - pis) + .5 * (np.log(tau) - np.log(vt))).astype(T))
+    shvt, mm = np.ascontiguousarray(np.sqrt(.5 * vt).astype(T)), np.ascontiguousarray((n / (vt * 0.8)).astype(T))
+    lnp = np.full(M, np.log(1 - pis.sum()), T)
+    ref = _incr_start(np.random.default_rng(9), M, T, "garbage", K)
+    got = _incr_start(np.random.default_rng(9), M, T, "garbage", K)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    for _ in range(3):
+        oracle_built.e_step_mixture(P["lb"], P["indptr"], P["data"], P["beta"], ref["var_gamma"], ref["var_mu"], ref["eta"],
+                                    ref["q"], ref["eta_diff"], lnp, u_logs, shvt, mm, P["dq"], 1, True)
+        vb.cpp_e_step_mixture_resident(ld, P["beta"], got["var_gamma"], got["var_mu"], got["eta"], got["q"], got["eta_diff"],
+                                       lnp, u_logs, shvt, mm, P["dq"], False)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= 1e-4, (k, relmax(got[k], ref[k]))
+    ld.destroy()

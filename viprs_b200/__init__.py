@@ -11,6 +11,7 @@ from .ld import DeviceLD  # noqa: F401
 from .e_step import (cpp_e_step, cpp_e_step_mixture, cpp_e_step_grid, e_step_device,  # noqa: F401
                      e_step_mixture_device, e_step_grid_device, q_offset_device,
                      cpp_e_step_resident, cpp_e_step_mixture_resident,
+                     e_step_incremental_device, e_step_mixture_incremental_device,
                      check_omp_support, check_blas_support)
 
 __version__ = "0.1.0"

@@ -48,6 +48,8 @@ SIGNATURES = {
     "viprs_b200_q_offset_f64": (ctypes.c_int, [_vp, _vp, _vp, _f64, _vp, _vp]),
     "viprs_b200_e_step_mixture_f32": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f32, _i32, _vp, _vp]),
     "viprs_b200_e_step_mixture_f64": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f64, _i32, _vp, _vp]),
+    "viprs_b200_e_step_incremental_f32": (ctypes.c_int, [_vp] * 10 + [_f32, _vp]),
+    "viprs_b200_e_step_mixture_incremental_f32": (ctypes.c_int, [_vp, _i32] + [_vp] * 10 + [_f32, _vp]),
     "viprs_b200_e_step_grid_f32": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f32, _vp]),
     "viprs_b200_e_step_grid_f64": (ctypes.c_int, [_vp, _i32, _i32] + [_vp] * 10 + [_f64, _vp]),
     "viprs_b200_backward_dot_f32": (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp]),

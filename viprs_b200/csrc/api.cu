@@ -29,6 +29,27 @@ struct DevBuf {            // scoped device allocation
     ~DevBuf() { cudaFree(d); }
 };
 
+// internal streams / events of the chunked host-state round trip, created once per device on first use
+struct HostStreams {
+    static constexpr int kMax = 8;
+    cudaStream_t s[kMax] = {};
+    cudaEvent_t join[kMax] = {};
+    cudaEvent_t fork = nullptr;
+    int n = 0;
+};
+HostStreams* host_streams(int n) {
+    static HostStreams per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || n > HostStreams::kMax) return nullptr;
+    HostStreams& h = per_dev[dev];
+    if (!h.fork && cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (; h.n < n; ++h.n) {
+        if (cudaStreamCreateWithFlags(&h.s[h.n], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&h.join[h.n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &h;
+}
+
 // One sweep with HOST state arrays on a device-resident LD matrix: upload what the reference's cpp_e_step* reads,
 // sweep, materialise q, download what it writes.  K == 0: cpp_e_step; K > 0: cpp_e_step_mixture.  The staging buffer
 // lives in the LD handle (grown on demand), so a per-iteration caller allocates nothing.
@@ -60,6 +81,58 @@ int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, c
     unsigned char *d_g = d + 6 * n1, *d_mu = d_g + nk, *d_ul = d_mu + nk, *d_sv = d_ul + nk, *d_mm = d_sv + nk;
     cudaError_t e = cudaSuccess;
     int rc = VIPRS_B200_OK;
+    // ---- float32, register-resident sweep: the reference's incremental q (no q offset, no vouching), in row chunks
+    // on internal streams -- chunk c's sweep overlaps chunk c+1's uploads and chunk c-1's downloads
+    if (ts == 4 && (K == 0 || K <= 4) && getenv("VIPRS_B200_NO_INCREMENTAL") == nullptr) {
+        using F = float;
+        const int nch = ld->n_chunks > 0 ? ld->n_chunks : 1;
+        HostStreams* hs = host_streams(nch);
+        if (hs) {
+            // all chunks wait for whatever the caller queued on `st`
+            if (e == cudaSuccess) e = cudaEventRecord(hs->fork, st);
+            bool unsupported = false;
+            for (int c = 0; c < nch && e == cudaSuccess && rc == 0; ++c) {
+                cudaStream_t sc = hs->s[c];
+                e = cudaStreamWaitEvent(sc, hs->fork, 0);
+                const size_t r0 = ld->n_chunks > 0 ? (size_t)ld->h_chunk_row[c] : 0;
+                const size_t r1 = ld->n_chunks > 0 ? (size_t)ld->h_chunk_row[c + 1] : (size_t)M;
+                const size_t o1 = r0 * ts, b1 = (r1 - r0) * ts, ok_ = o1 * kk, bk = b1 * kk;
+                auto upc = [&](unsigned char* dst, const void* src, size_t off, size_t n) {
+                    if (e == cudaSuccess && src && n)
+                        e = cudaMemcpyAsync(dst + off, reinterpret_cast<const unsigned char*>(src) + off, n, cudaMemcpyHostToDevice, sc);
+                };
+                upc(d_beta, std_beta, o1, b1); upc(d_eta, eta, o1, b1); upc(d_q, q, o1, b1);
+                if (K > 0) upc(d_lnp, log_null_pi, o1, b1);
+                upc(d_g, var_gamma, ok_, bk); upc(d_mu, var_mu, ok_, bk); upc(d_ul, u_logs, ok_, bk); upc(d_sv, shvt, ok_, bk);
+                upc(d_mm, mu_mult, ok_, bk);
+                if (e != cudaSuccess) break;
+                const int chunk = ld->n_chunks > 0 ? c : -1;
+                rc = K > 0 ? vb::incr_mix_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_lnp,
+                                              (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc)
+                           : vb::incr_slab_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
+                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc);
+                if (rc == VIPRS_B200_EUNSUPPORTED && c == 0) { unsupported = true; rc = 0; break; }
+                auto downc = [&](void* dst, unsigned char* src, size_t off, size_t n) {
+                    if (e == cudaSuccess && rc == 0 && n)
+                        e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(dst) + off, src + off, n, cudaMemcpyDeviceToHost, sc);
+                };
+                downc(var_gamma, d_g, ok_, bk); downc(var_mu, d_mu, ok_, bk); downc(eta, d_eta, o1, b1); downc(q, d_q, o1, b1);
+                downc(eta_diff, d_diff, o1, b1);
+                if (e == cudaSuccess) e = cudaEventRecord(hs->join[c], sc);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hs->join[c], 0);
+            }
+            if (!unsupported) {
+                cudaError_t e2 = cudaStreamSynchronize(st);
+                for (int c = 0; c < nch; ++c) cudaStreamSynchronize(hs->s[c]);
+                if (e == cudaSuccess) e = e2;
+                if (rc) return rc;
+                return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+            }
+            // nothing was launched: chunk 0 reported that the incremental sweep does not cover this LD / model
+            cudaStreamSynchronize(hs->s[0]);
+            e = cudaSuccess;
+        }
+    }
     auto up = [&](void* dst, const void* src, size_t n) {
         if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
     };

@@ -63,14 +63,14 @@ static int launch_one(const viprs_b200_ld* ld, const SweepPlan& p, const RingGeo
 }
 
 // register-resident kernel (float32 state, LD blocks <= 4096 SNPs, two CTAs per SM)
-template <typename U, typename Model, int NLIMB, int VER>
+template <typename U, typename Model, int NLIMB, int VER, bool INCR = false>
 static int launch_fast_ver(const viprs_b200_ld* ld, SweepPlan p, const typename Model::Args& ma,
                            const StateArgs<float>& sa, cudaStream_t st) {
     const RingGeometry g = fast_ring_geometry(ld);
     const FastLayout FL = make_fast_layout(ld->stage_bytes, g.nst);
     p.nst = g.nst;
     p.L.stages = FL.stages;
-    auto kern = sweep_fast_kernel<U, Model, NLIMB, VER>;
+    auto kern = sweep_fast_kernel<U, Model, NLIMB, VER, INCR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL.total);
     if (e != cudaSuccess) return (int)e;
     return launch_traced(p, st, [&](const SweepPlan& pp) {
@@ -96,14 +96,27 @@ static bool fast_path_ok(const viprs_b200_ld* ld) {
     return ld->max_block <= FAST_MAX_BLOCK && fast_ring_geometry(ld).nst >= 3 && env_int("VIPRS_B200_FORCE_GENERIC", 0) == 0;
 }
 
-// one launch over the sweep units of phase `ph` (all units when the LD has a single phase)
+// A subset of the sweep units of a single-phase LD: row chunk `chunk` of the handle (ld.h), or everything (chunk < 0).
+struct UnitSubset {
+    const int32_t* order; int count; int item0, item1; int row0, row1;
+};
+static UnitSubset unit_subset(const viprs_b200_ld* ld, int chunk) {
+    if (chunk < 0 || ld->n_chunks <= 0)
+        return UnitSubset{ld->d_blk_order, ld->n_blocks, 0, ld->n_items_bwd, 0, ld->M};
+    const int u0 = ld->h_chunk_unit[chunk], u1 = ld->h_chunk_unit[chunk + 1];
+    return UnitSubset{ld->d_chunk_order + u0, u1 - u0, ld->h_chunk_item[chunk], ld->h_chunk_item[chunk + 1],
+                      ld->h_chunk_row[chunk], ld->h_chunk_row[chunk + 1]};
+}
+
+// one launch over the sweep units of phase `ph` (all units when the LD has a single phase), or over `sub`
 template <typename T, typename U, typename Model>
-static int launch_phase(const viprs_b200_ld* ld, int ph, const typename Model::Args& ma, const StateArgs<T>& sa, cudaStream_t st) {
+static int launch_phase(const viprs_b200_ld* ld, int ph, const typename Model::Args& ma, const StateArgs<T>& sa, cudaStream_t st,
+                        const UnitSubset* sub = nullptr) {
     SweepPlan p;
     RingGeometry g;
-    const int first = ld->h_phase_ptr[ph], count = ld->h_phase_ptr[ph + 1] - first;
+    const int first = ld->h_phase_ptr[ph], count = sub ? sub->count : ld->h_phase_ptr[ph + 1] - first;
     if (count <= 0) return VIPRS_B200_OK;
-    auto phase_of = [&](SweepPlan& q) { q.blk_order = ld->d_blk_order + first; q.n_blocks = count; };
+    auto phase_of = [&](SweepPlan& q) { q.blk_order = sub ? sub->order : ld->d_blk_order + first; q.n_blocks = count; };
     if constexpr (sizeof(T) == 4 && !Model::kHeavy && sizeof(U) != 8) {
         if (fast_path_ok<T, U, Model>(ld)) {
             make_plan(ld, (int)sizeof(T), p, g);        // ring fields are overridden by the fast launcher
@@ -167,11 +180,12 @@ __global__ void scale_copy_kernel(int M, const T* __restrict__ src, T scale, T* 
 // q_offset (nullable, q units): a caller-supplied constant part of q (see viprs_b200_q_offset_*).
 template <typename T, typename U, typename Model>
 static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma, StateArgs<T> sa, const T* q_offset, T dq,
-                        cudaStream_t st) {
+                        cudaStream_t st, const UnitSubset* sub = nullptr) {
     if (ld->n_phases == 1 && ld->ext_elems == 0) {
         if (q_offset) { sa.fext = q_offset; sa.fscale = T(1) / dq; }
-        return launch_phase<T, U, Model>(ld, 0, ma, sa, st);
+        return launch_phase<T, U, Model>(ld, 0, ma, sa, st, sub);
     }
+    if (sub) return VIPRS_B200_EUNSUPPORTED;
     T* fext = reinterpret_cast<T*>(ld->d_fext);
     T* bext = reinterpret_cast<T*>(ld->d_bext);
     const int M = ld->M;
@@ -240,6 +254,68 @@ static int e_step_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_ga
         if (rc == 0 && materialize_q) rc = launch_backward<T, U>(ld, eta, q, dq, st);
         return rc;
     });
+}
+
+// The reference's own q bookkeeping on device arrays (cpp_e_step / cpp_e_step_mixture semantics exactly, q in/out):
+//   sweep:  q_j used at step j = q_in[j] + dq sum_{i<j} R_ij eta_diff_i           (e_step.hpp:421)
+//   after:  q[j] += dq sum_{k>j} R_jk eta_diff_k                                  (update_q_factor, :435-440)
+// Register-resident kernel only (float32 state, LD blocks <= 4096 SNPs, one phase): no backward dots inside the sweep,
+// two reads of the LD per call like the reference.  `chunk` >= 0 restricts the call to one row chunk of the handle.
+template <typename U, typename Model>
+static int launch_incremental(const viprs_b200_ld* ld, const typename Model::Args& ma, StateArgs<float> sa, float dq, int chunk,
+                              cudaStream_t st) {
+    using T = float;
+    if constexpr (Model::kHeavy || sizeof(U) == 8) {
+        return VIPRS_B200_EUNSUPPORTED;
+    } else {
+        if (!fast_path_ok<T, U, Model>(ld) || ld->n_phases != 1 || ld->ext_elems != 0) return VIPRS_B200_EUNSUPPORTED;
+        if (chunk >= ld->n_chunks && chunk >= 0) return VIPRS_B200_EINVAL;
+        const UnitSubset sub = unit_subset(ld, chunk);
+        if (sub.count <= 0) return VIPRS_B200_OK;
+        SweepPlan p;
+        RingGeometry g;
+        make_plan(ld, (int)sizeof(T), p, g);
+        p.blk_order = sub.order; p.n_blocks = sub.count;
+        sa.fext = sa.q; sa.fscale = T(1) / dq;        // q_in: read by the chain 32 rows ahead of where it writes q
+        int rc;
+        if (std::is_same<U, int8_t>::value) rc = launch_fast_ver<U, Model, 3, 1, true>(ld, p, ma, sa, st);
+        else rc = launch_fast_ver<U, Model, 4, 1, true>(ld, p, ma, sa, st);
+        if (rc == 0)
+            rc = launch_row_dots<T, U>(ld->d_items_bwd + sub.item0, sub.item1 - sub.item0, ld->d_packed, ld->d_prow, ld->d_pcs,
+                                       sa.eta_diff, sa.q, dq, st);
+        return rc;
+    }
+}
+
+template <typename T>
+static int e_step_incremental_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
+                                       T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq, int chunk,
+                                       cudaStream_t st) {
+    if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
+        return VIPRS_B200_EINVAL;
+    if constexpr (sizeof(T) != 4) {
+        return VIPRS_B200_EUNSUPPORTED;
+    } else {
+        typename SlabModel<T>::Args ma{std_beta, u_logs, shvt, mu_mult, var_gamma, var_mu, dq};
+        StateArgs<T> sa{eta, q, eta_diff};
+        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), SlabModel<T>>(ld, ma, sa, dq, chunk, st); });
+    }
+}
+
+template <typename T>
+static int mixture_incremental_dispatch(const viprs_b200_ld* ld, int K, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
+                                        T* eta_diff, const T* log_null_pi, const T* u_logs, const T* shvt, const T* mu_mult,
+                                        T dq, int chunk, cudaStream_t st) {
+    if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !log_null_pi || !u_logs || !shvt || !mu_mult)
+        return VIPRS_B200_EINVAL;
+    if constexpr (sizeof(T) != 4) {
+        return VIPRS_B200_EUNSUPPORTED;
+    } else {
+        if (K < 1 || K > 4) return VIPRS_B200_EUNSUPPORTED;
+        typename MixModel<T, 4>::Args ma{std_beta, u_logs, shvt, mu_mult, log_null_pi, var_gamma, var_mu, dq, K};
+        StateArgs<T> sa{eta, q, eta_diff};
+        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), MixModel<T, 4>>(ld, ma, sa, dq, chunk, st); });
+    }
 }
 
 // Sweep with the M-step / ELBO reductions fused into its output role (register-resident kernel version 2, float32

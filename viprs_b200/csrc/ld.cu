@@ -240,16 +240,21 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         const int nlb = (int)ldblk_row.size() - 1;
 
         // ---- sweep units: an LD block, or kTileRows-row tiles of a block larger than kTileLimit -----------
+        // (VIPRS_B200_TILE_LIMIT / VIPRS_B200_TILE_ROWS: timing experiments with the blocked decomposition on blocks that
+        // would fit one unit)
+        int tile_limit = vb::kTileLimit, tile_rows = vb::kTileRows;
+        if (const char* e = getenv("VIPRS_B200_TILE_LIMIT")) { const int v = atoi(e); if (v >= 64 && v <= vb::kTileLimit) tile_limit = v; }
+        if (const char* e = getenv("VIPRS_B200_TILE_ROWS")) { const int v = atoi(e); if (v >= 64 && v <= vb::kTileRows && v % 16 == 0) tile_rows = v; }
         std::vector<int32_t> blk_row, unit_phase;
         int32_t max_ld_block = 0, n_phases = 1;
         for (int b = 0; b < nlb; ++b) {
             const int r0 = ldblk_row[b], r1 = ldblk_row[b + 1], B = r1 - r0;
             max_ld_block = std::max(max_ld_block, B);
-            if (B <= vb::kTileLimit) {
+            if (B <= tile_limit) {
                 blk_row.push_back(r0); unit_phase.push_back(0);
             } else {
                 int ph = 0;
-                for (int t = r0; t < r1; t += vb::kTileRows) { blk_row.push_back(t); unit_phase.push_back(ph++); }
+                for (int t = r0; t < r1; t += tile_rows) { blk_row.push_back(t); unit_phase.push_back(ph++); }
                 n_phases = std::max(n_phases, ph);
             }
         }
@@ -381,6 +386,33 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         }
         h->n_items_bwd = (int32_t)items_bwd.size();
         h->n_items_bwd_ext = (int32_t)items_bwd_ext.size();
+        // row chunks of about equal sweep cost (single-phase LD with enough units)
+        std::vector<int32_t> chunk_order;
+        if (n_phases == 1 && nb >= 2 * vb::kChunks) {
+            double total = 0.0;
+            for (int b = 0; b < nb; ++b) total += (double)blk_cost[b];
+            h->h_chunk_unit.assign(1, 0);
+            double run = 0.0;
+            for (int b = 0; b < nb; ++b) {
+                run += (double)blk_cost[b];
+                const int c = (int)h->h_chunk_unit.size();
+                if (c < vb::kChunks && run >= total * c / vb::kChunks && b + 1 < nb) h->h_chunk_unit.push_back(b + 1);
+            }
+            h->h_chunk_unit.push_back(nb);
+            h->n_chunks = (int32_t)h->h_chunk_unit.size() - 1;
+            chunk_order.resize(nb);
+            std::iota(chunk_order.begin(), chunk_order.end(), 0);
+            size_t it = 0;
+            for (int c = 0; c < h->n_chunks; ++c) {
+                const int u0 = h->h_chunk_unit[c], u1 = h->h_chunk_unit[c + 1];
+                std::stable_sort(chunk_order.begin() + u0, chunk_order.begin() + u1, [&](int a, int b) { return blk_cost[a] > blk_cost[b]; });
+                h->h_chunk_row.push_back(blk_row[u0]);
+                while (it < items_bwd.size() && items_bwd[it].x < blk_row[u0]) ++it;
+                h->h_chunk_item.push_back((int32_t)it);
+            }
+            h->h_chunk_row.push_back(M);
+            h->h_chunk_item.push_back((int32_t)items_bwd.size());
+        }
 
         // ---- device arrays ------------------------------------------------------------------
         CUDA_TRY(cudaMalloc(&h->d_packed, (size_t)std::max<int64_t>(off, 16) * esize + 64));
@@ -408,6 +440,10 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         CUDA_TRY(cudaMemcpyAsync(h->d_panel_row, panel_row.data(), sizeof(int32_t) * (np + 1), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_panel_need, panel_need.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(h->d_blk_order, order.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, stream));
+        if (h->n_chunks > 0) {
+            CUDA_TRY(cudaMalloc(&h->d_chunk_order, sizeof(int32_t) * nb));
+            CUDA_TRY(cudaMemcpyAsync(h->d_chunk_order, chunk_order.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, stream));
+        }
         CUDA_TRY(cudaMemcpyAsync(h->d_items_diag, items_diag.data(), sizeof(int4) * nb, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(int64_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(d_cs, cs.data(), sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, stream));
@@ -534,7 +570,7 @@ extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext); cudaFree(h->d_items_bwd); cudaFree(h->d_items_bwd_ext);
     cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws); cudaFree(h->d_unit_partial);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
-    cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order);
+    cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order); cudaFree(h->d_chunk_order);
     delete h;
     return VIPRS_B200_OK;
 }

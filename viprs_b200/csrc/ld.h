@@ -37,6 +37,13 @@ struct viprs_b200_ld {
     std::vector<int32_t> h_blk_row;     // host copy of the sweep-unit boundaries
     std::vector<int32_t> h_ldblk_row;   // [n_ld_blocks+1] LD-block boundaries, for callers (sharding across GPUs)
     std::vector<int32_t> h_phase_ptr;   // [n_phases+1] slice of d_blk_order swept by launch p
+    // Row chunks (single-phase LD only): contiguous runs of sweep units of about equal cost, so that a caller with HOST
+    // state can overlap the copies of one chunk with the sweep of another (viprs_b200_cpp_e_step_resident).
+    int32_t n_chunks = 0;
+    int32_t* d_chunk_order = nullptr;      // [n_blocks] unit ids grouped by chunk, most expensive first inside a chunk
+    std::vector<int32_t> h_chunk_unit;     // [n_chunks+1] slice of d_chunk_order (= unit range, units are in row order)
+    std::vector<int32_t> h_chunk_row;      // [n_chunks+1] first row of every chunk
+    std::vector<int32_t> h_chunk_item;     // [n_chunks+1] slice of d_items_bwd
 
     // ---- tiled LD blocks (blocks larger than kTileLimit rows, e.g. 10,240-SNP float64 blocks or banded LD) ----
     // Row j of tile [t0, t1) keeps its columns (j, t1) in the packed layout above (the sequential part, swept by the
@@ -71,6 +78,7 @@ struct viprs_b200_ld {
 namespace vb {
 constexpr int kTileLimit = 4096;   // LD blocks up to this many rows are one sweep unit
 constexpr int kTileRows = 2048;    // tile size of larger blocks (fits the float64 state of the generic kernel)
+constexpr int kChunks = 4;         // row chunks for copy / sweep overlap of host-state callers
 // shared memory per CTA that lets two CTAs share one SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr int kSmemTwoPerSM = 113 * 1024;
 struct RingGeometry { int nst; int smem_bytes; int ctas_per_sm; };
@@ -80,4 +88,12 @@ RingGeometry ring_geometry(const viprs_b200_ld* ld, int tsize);
 RingGeometry fast_ring_geometry(const viprs_b200_ld* ld);
 // build the dense symmetric block layout if it does not exist yet; 0 or an error code
 int ensure_dense(const viprs_b200_ld* ld, cudaStream_t stream);
+// incremental-q sweeps of one row chunk (chunk < 0: everything), see launch.cuh launch_incremental; defined in
+// slab_f32.cu / mix_f32.cu, used by the host-state drop-ins in api.cu
+int incr_slab_f32(const viprs_b200_ld* ld, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
+                  float* eta_diff, const float* u_logs, const float* shvt, const float* mu_mult, float dq, int chunk,
+                  cudaStream_t st);
+int incr_mix_f32(const viprs_b200_ld* ld, int K, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
+                 float* eta_diff, const float* log_null_pi, const float* u_logs, const float* shvt, const float* mu_mult,
+                 float dq, int chunk, cudaStream_t st);
 }  // namespace vb

@@ -27,3 +27,18 @@ extern "C" int viprs_b200_e_step_fused_f32(const viprs_b200_ld_t* ld, const floa
     return vb::e_step_fused_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau,
                                             mu_mult, dq_scale, n_per_snp, theta, nseg, seg_ptr, sums, (cudaStream_t)stream);
 }
+
+int vb::incr_slab_f32(const viprs_b200_ld* ld, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
+                      float* eta_diff, const float* u_logs, const float* shvt, const float* mu_mult, float dq, int chunk,
+                      cudaStream_t st) {
+    return vb::e_step_incremental_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq,
+                                                  chunk, st);
+}
+
+extern "C" int viprs_b200_e_step_incremental_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,
+                                                 float* var_mu, float* eta, float* q, float* eta_diff, const float* u_logs,
+                                                 const float* sqrt_half_var_tau, const float* mu_mult, float dq_scale,
+                                                 void* stream) {
+    return vb::incr_slab_f32(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult, dq_scale, -1,
+                             (cudaStream_t)stream);
+}

@@ -366,7 +366,10 @@ __device__ __forceinline__ void producer_role(const SweepPlan& p, unsigned char*
 
 // NA / NC: number of bulk warps that publish a_prog / c_prog (and dot partials)
 // NW: warps that only publish a progress counter the chain waits on like an A counter (prog layout: A | W | C)
-template <typename T, typename Model, int NA, int NC, int NW = 0, typename W = T>
+// INCR: the reference's own bookkeeping of q (e_step.hpp:421, 435-440) -- the forward axpys carry eta_diff instead of
+// eta_new and the caller's q enters through fext, so that X = q_in / dq + sum_{i<j} R_ij eta_diff_i with no backward
+// dots at all; the backward part is added to q by a second pass over the LD (update_q_factor) after the sweep.
+template <typename T, typename Model, int NA, int NC, int NW = 0, typename W = T, bool INCR = false>
 __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Model::Args& ma, const StateArgs<T>& sa,
                                            const SmemView<T>& sm, int r0, int B, int pan0, int NP, int lane) {
     const int NST = p.nst;
@@ -443,7 +446,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
                     Xown = mine ? X0 : Xown;
                     const T x0n = mine ? X1 : X0;          // the window slides by one column: independent of the shuffle
                     const T x1n = mine ? T(0) : X1;
-                    const T a = shfl_t(en, (base + h + i) & 31);
+                    const T a = shfl_t(INCR ? (skip ? T(0) : d) : en, (base + h + i) & 31);
                     X0 = fma_t(w0[i], a, x0n);             // :421 restricted to the window
                     X1 = fma_t(w1[i], a, x1n);
                 };
@@ -471,7 +474,7 @@ __device__ __forceinline__ void chain_role(const SweepPlan& p, const typename Mo
             if (!skip) sa.eta[row] = en;                                       // :431
             sa.eta_diff[row] = skip ? T(0) : d;                                // :413 / :418
             sa.q[row] = dq * (Xown - bsum);                                    // forward part of q (see header)
-            sts_t(a_alpha + (uint32_t)(cl & (RR - 1)) * sizeof(T), en);
+            sts_t(a_alpha + (uint32_t)(cl & (RR - 1)) * sizeof(T), INCR ? (skip ? T(0) : d) : en);
         }
         __syncwarp();
         if (lane == 0) {

@@ -97,7 +97,9 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {      // 
 constexpr int FAST_OUTPUT_WARP = FAST_WARPS;
 template <int VER> constexpr int fast_threads() { return (VER == 2 ? FAST_WARPS + 1 : FAST_WARPS) * WARP; }
 
-template <typename U, typename Model, int NLIMB, int VER>
+// INCR (version 1 only): q maintained incrementally like the reference (see chain_role) -- the A warps only cut the
+// window coefficients, their backward dots are skipped.
+template <typename U, typename Model, int NLIMB, int VER, bool INCR = false>
 __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(const SweepPlan p, const FastLayout FL,
                                                                               const typename Model::Args ma,
                                                                               const StateArgs<float> sa) {
@@ -155,7 +157,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
     [[maybe_unused]] uint32_t hl[NVT][DP4A ? NLIMB : 1][4];
     [[maybe_unused]] float es[DP4A ? 1 : NVT][DP4A ? 1 : EPV];
     [[maybe_unused]] double wscale = 1.0;                // value of one fixed-point unit: bscale * 2^-(7 NLIMB - 1)
-    if constexpr (DP4A) {
+    if constexpr (INCR) {
+        // no backward dots: nothing of eta_old is needed
+    } else if constexpr (DP4A) {
         float mx = 0.f;
         for (int i = tid; i < B; i += blockDim.x) mx = fmaxf(mx, fabsf(sa.eta[r0 + i]));
 #pragma unroll
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
         if constexpr (VER == 2) output_role<T, Model>(p, ma, sa, orr, r0, pan0, NP, lane, blk);
     } else if (warp == FAST_CHAIN_WARP) {
         if constexpr (VER == 2) chain_role2<T, Model, NAW, NCW>(p, ma, sa, sm, orr, r0, B, pan0, NP, lane);
-        else chain_role<T, Model, NAW, NCW, NWW>(p, ma, sa, sm, r0, B, pan0, NP, lane);
+        else chain_role<T, Model, NAW, NCW, NWW, T, INCR>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else if (ai >= 0) {
         // =============================== A: backward dots =====================================
         // Per panel every owned tile is classified (warp-uniform): dead (no row of the panel stores it), interior
@@ -286,8 +290,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
 #ifdef VB_WHATIF_SKIP_A
             anyl = false;                    // timing experiment: no backward-dot arithmetic (results are wrong)
 #endif
+            if constexpr (INCR) anyl = false;
             if (!anyl) {
-                if constexpr (!DP4A) {
+                if constexpr (!DP4A || INCR) {
                     if (lane < P) sm.partial[wa * RR + ((jl0 + lane) & (RR - 1))] = 0.f;
                 }
             } else {
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                 }
             }
             trace_ev(p, lane, wa, 6, u);
-            if constexpr (DP4A) {
+            if constexpr (DP4A && !INCR) {
                 // lane r < P: recombine the digits of row r in int64.  sum_b u8 * digit = sum code * digit +
                 // 128 * sum digit over the row's packed range; the range term (128 * sum of Q over the range, from
                 // the prefix array) is removed once per row, by A warp 0.

@@ -93,6 +93,42 @@ def e_step_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqr
     _lib.check(rc, "viprs_b200_e_step")
 
 
+def e_step_incremental_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult,
+                              dq_scale):
+    """
+    cpp_e_step (e_step_cpp.pyx:91-122) on float32 CUDA tensors with the reference's own incremental bookkeeping of q
+    (e_step.hpp:421, 435-440): q is in/out, whatever it holds on entry is honoured.  Raises ViprsB200Error
+    (VIPRS_B200_EUNSUPPORTED) where the register-resident sweep does not apply.
+    """
+    L = _lib.lib()
+    ts = (std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, sqrt_half_var_tau, mu_mult)
+    for t in ts:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == ld.M):
+            raise ValueError("e_step_incremental_device: arrays must be contiguous float32 CUDA tensors of length M")
+    rc = L.viprs_b200_e_step_incremental_f32(ld.handle, *[t.data_ptr() for t in ts], float(dq_scale), _stream_ptr())
+    _lib.check(rc, "viprs_b200_e_step_incremental_f32")
+
+
+def e_step_mixture_incremental_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
+                                      sqrt_half_var_tau, mu_mult, dq_scale):
+    """cpp_e_step_mixture (e_step_cpp.pyx:125-159) on float32 CUDA tensors, q in/out and incremental (K <= 4)."""
+    L = _lib.lib()
+    if var_mu.dim() != 2:
+        raise ValueError("e_step_mixture_incremental_device: var_mu must be (M, K)")
+    K = var_mu.shape[1]
+    for t in (var_gamma, var_mu, u_logs, sqrt_half_var_tau, mu_mult):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == (ld.M, K)):
+            raise ValueError("e_step_mixture_incremental_device: (M,K) arrays must be C-contiguous float32 CUDA tensors")
+    for t in (std_beta, eta, q, eta_diff, log_null_pi):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == ld.M):
+            raise ValueError("e_step_mixture_incremental_device: (M,) arrays must be contiguous float32 CUDA tensors")
+    rc = L.viprs_b200_e_step_mixture_incremental_f32(
+        ld.handle, K, std_beta.data_ptr(), var_gamma.data_ptr(), var_mu.data_ptr(), eta.data_ptr(), q.data_ptr(),
+        eta_diff.data_ptr(), log_null_pi.data_ptr(), u_logs.data_ptr(), sqrt_half_var_tau.data_ptr(), mu_mult.data_ptr(),
+        float(dq_scale), _stream_ptr())
+    _lib.check(rc, "viprs_b200_e_step_mixture_incremental_f32")
+
+
 def e_step_mixture_device(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
                           sqrt_half_var_tau, mu_mult, dq_scale, materialize_q=True, q_offset=None):
     """One mixture sweep on a DeviceLD; (M,K) arrays are C-order CUDA tensors, the rest have M entries."""
