@@ -464,6 +464,43 @@ def run_workload(name, wl, steps, warmup, rank, world, local_rank, scaling, dist
     return out
 
 
+def multi_gpu_parity(rank, world):
+    """N > 1 only (the driver's GPU test box has one GPU, so tests/test_multi_gpu.py is skipped there): 8 EM iterations of
+    VIPRS on a small fixed genome (two chromosomes, ragged LD blocks), sharded over the ranks of this run with one
+    all-reduce per iteration, against the same iterations on rank 0 alone.  Outside every timed region."""
+    import torch
+    from viprs_b200 import synth
+    from viprs_b200.model import VIPRS
+    sizes = [700, 512, 900, 333, 1200, 64, 800, 1024, 256, 2048, 96, 640, 1500, 300, 450, 777]
+    inp = synth.make_inputs(sizes, ld_dtype="int8", float_dtype=torch.float32, device="cpu", seed=11, n=50000)
+    half = sum(sizes[:8])
+    ip, lb = inp["ld_indptr"].numpy(), inp["ld_left_bound"].numpy()
+
+    def chrom(r0, r1):
+        return dict(ld_data=inp["ld_data"].numpy()[ip[r0]:ip[r1]], ld_indptr=(ip[r0:r1 + 1] - ip[r0]),
+                    ld_left_bound=(lb[r0:r1] - r0).astype(np.int32), std_beta=inp["std_beta"].numpy()[r0:r1],
+                    n_per_snp=inp["n_per_snp"].numpy()[r0:r1])
+
+    data = {1: chrom(0, half), 2: chrom(half, sum(sizes))}
+
+    def history(shard):
+        m = VIPRS(data=data, float_precision="float32", shard=shard)
+        m.initialize({"pi": 0.02, "sigma_epsilon": 0.8})
+        h = []
+        for _ in range(8):
+            m.e_step(); m.m_step()
+            h.append([m.elbo(), float(m.pi), float(m.sigma_epsilon), float(m.tau_beta), m.max_eta_diff()])
+        return np.array(h)
+
+    sharded = history(True)
+    if rank != 0:
+        return None
+    alone = history(False)
+    err = float(np.max(np.abs(alone - sharded) / np.maximum(np.abs(alone), 1e-30)))
+    return {"what": "8 EM iterations (ELBO, pi, sigma_epsilon, tau_beta, max|eta_diff|) of VIPRS on a %d-SNP genome sharded "
+                    "over %d GPUs vs the same on one GPU" % (sum(sizes), world), "max_rel_diff": err, "tolerance": 1e-12, "ok": bool(err <= 1e-12)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -528,6 +565,13 @@ def main():
             except Exception as ex:          # an extra must never take the headline down with it
                 extras[nm] = {"error": repr(ex)[:300]}
 
+    mgp = None
+    if world > 1 and not args.no_extras:
+        try:
+            mgp = multi_gpu_parity(rank, world)
+        except Exception as ex:
+            mgp = {"error": repr(ex)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b = cpu_reference_leg(args.workload, wl, 10, 1, os.cpu_count() or 1, max_seconds=20.0)
@@ -551,6 +595,8 @@ def main():
         line["roofline"]["kernel_ms_source"] = main_res["kernel_ms_source"]
         if extras:
             line["workloads"] = extras
+        if mgp is not None:
+            line["multi_gpu_parity"] = mgp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
