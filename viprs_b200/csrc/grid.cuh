@@ -57,7 +57,7 @@ template <> struct GridT<double> { static constexpr int GT = 4; };
 
 constexpr int GPB = 3;            // depth (panels) of the parameter / window / output rings between the stager warp and the chain
 
-struct GridLayout { uint32_t stages, wwin, wraw, pbuf, obuf, alpha, qpub, bars, prog, total; };
+struct GridLayout { uint32_t stages, wwin, wraw, pbuf, obuf, ybuf, alpha, qpub, bars, prog, total; };
 inline GridLayout make_grid_layout(int tsize, int gt, int stage_bytes, int nst) {
     GridLayout L;
     uint32_t o = 0;
@@ -66,6 +66,7 @@ inline GridLayout make_grid_layout(int tsize, int gt, int stage_bytes, int nst) 
     L.wraw = o;   o += (uint32_t)GP * GWW * 8u;                       // raw window, sized for 8-byte LD elements
     L.pbuf = o;   o += (uint32_t)GPB * 6u * GP * (uint32_t)gt * (uint32_t)tsize;
     L.obuf = o;   o += (uint32_t)GPB * 2u * GP * (uint32_t)gt * (uint32_t)tsize;
+    L.ybuf = o;   o += 2u * GP * (uint32_t)gt * (uint32_t)tsize;                // chain hand-over between its two warps
     L.alpha = o;  o += (uint32_t)GAR * GP * (uint32_t)gt * (uint32_t)tsize;
     L.qpub = o;   o += 2u * GP * (uint32_t)gt * (uint32_t)tsize;
     L.bars = o;   o += (2u * GNST_MAX + GAR) * 8u;
@@ -349,15 +350,28 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
             __syncwarp();                                       // every lane has read its slots of ring entry u % GPB
             if (u + GPB < NP) stage(u + GPB);
         }
-      } else if (warp == aux0 + 1) {
+      } else if (warp == aux0 + 1 || warp == aux0 + 3) {
         // =============================== chain ===============================================
+        // Two warps on different SM sub-partitions take the panels in turns (even / odd): the two bulk warps that share a
+        // sub-partition with the chain set the pace of the whole CTA through the 2-panel window, so the chain's issue
+        // slots are spread over two sub-partitions.  The carry between panels (Y: corrections to the next panel's own
+        // columns) goes through shared memory; the hand-over is the cdone barrier of the previous panel.
+        const int which = (warp - aux0 - 1) >> 1;
+        const uint32_t a_ybuf = sbase + p.L.ybuf;
+        auto yslot = [&](int u) { return a_ybuf + (uint32_t)((((u & 1) * GT + g) * GP + RPL * w) * sizeof(T)); };
         const T dq = a.dq;
         T mm[RPL], ul[RPL], hm[RPL], bt[RPL], ndqeo[RPL];
         T X[RPL], Y[RPL];
-#pragma unroll
-        for (int m = 0; m < RPL; ++m) { X[m] = T(0); Y[m] = T(0); }
-        for (int u = 0; u < NP; ++u) {
+        for (int u = which; u < NP; u += 2) {
             const int j0 = u * GP;
+            if (u > 0) {
+                mbar_wait_a(a_cdone + 8u * (uint32_t)((u - 1) % GAR), ((u - 1) / GAR) & 1);
+                const uint4 y4 = lds128(yslot(u - 1));
+                memcpy(Y, &y4, 16);
+            } else {
+#pragma unroll
+                for (int m = 0; m < RPL; ++m) Y[m] = T(0);
+            }
             // the stager has made panel u ready; every bulk warp has applied (and published past) panel u-2
             {
                 uint32_t spins = 0;
@@ -428,7 +442,8 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
                 sts_t(a_alpha + (uint32_t)((((u % GAR) * GP + RPL * w + m) * GT + g) * sizeof(T)), o_al[m]);
             { uint4 t4;
               memcpy(&t4, o_mu, 16); sts128(oslot(u, 0), t4);
-              memcpy(&t4, o_g, 16); sts128(oslot(u, 1), t4); }
+              memcpy(&t4, o_g, 16); sts128(oslot(u, 1), t4);
+              memcpy(&t4, Y, 16); sts128(yslot(u), t4); }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(a_cdone + 8u * (uint32_t)(u % GAR));
         }
@@ -456,9 +471,32 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         auto q_load = [&](int col, int g) -> T {
             return (col < B && gval[g]) ? a.q[(size_t)gcol[g] * M + (size_t)r0 + col] : T(0);
         };
+        // float32: a thread's EPV columns of one grid column are EPV * 4 contiguous bytes (column-major state): 128-bit
+        // loads / stores when the whole vector lies inside the block and the addresses are 16-byte aligned
+        [[maybe_unused]] const bool q_vec_ok = F32 && (EPV % 4 == 0) && ((reinterpret_cast<size_t>(a.q) % 16) == 0) &&
+                                               (M % 4 == 0) && (r0 % 4 == 0);
 #pragma unroll
         for (int i = 0; i < NVT; ++i) {
             const int col0 = (t + NT * i) * EPV;
+            if constexpr (F32 && (EPV % 4 == 0)) {
+                if (q_vec_ok && col0 + EPV <= B) {
+#pragma unroll
+                    for (int g = 0; g < GT; ++g) {
+                        const float4* src = reinterpret_cast<const float4*>(a.q + (size_t)gcol[g] * M + (size_t)r0 + col0);
+#pragma unroll
+                        for (int e4 = 0; e4 < EPV / 4; ++e4) {
+                            const float4 v4 = gval[g] ? src[e4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (g & 1) qr[i][4 * e4 + k][g / 2].y = vv[k];
+                                else qr[i][4 * e4 + k][g / 2].x = vv[k];
+                            }
+                        }
+                    }
+                    continue;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
 #pragma unroll
@@ -570,6 +608,23 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
 #pragma unroll
         for (int i = 0; i < NVT; ++i) {
             const int col0 = (t + NT * i) * EPV;
+            if constexpr (F32 && (EPV % 4 == 0)) {
+                if (q_vec_ok && col0 + EPV <= B) {
+#pragma unroll
+                    for (int g = 0; g < GT; ++g) {
+                        if (!gval[g]) continue;
+                        float4* dst = reinterpret_cast<float4*>(a.q + (size_t)gcol[g] * M + (size_t)r0 + col0);
+#pragma unroll
+                        for (int e4 = 0; e4 < EPV / 4; ++e4) {
+                            float vv[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) vv[k] = (g & 1) ? qr[i][4 * e4 + k][g / 2].y : qr[i][4 * e4 + k][g / 2].x;
+                            dst[e4] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        }
+                    }
+                    continue;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < EPV; ++e) {
                 const int col = col0 + e;

@@ -388,7 +388,9 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         h->n_items_bwd_ext = (int32_t)items_bwd_ext.size();
         // row chunks of about equal sweep cost (single-phase LD with enough units)
         std::vector<int32_t> chunk_order;
-        if (n_phases == 1 && nb >= 2 * vb::kChunks) {
+        int n_chunks_want = vb::kChunks;
+        if (const char* e = getenv("VIPRS_B200_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 8) n_chunks_want = v; }
+        if (n_phases == 1 && nb >= 2 * n_chunks_want && n_chunks_want > 1) {
             double total = 0.0;
             for (int b = 0; b < nb; ++b) total += (double)blk_cost[b];
             h->h_chunk_unit.assign(1, 0);
@@ -396,7 +398,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
             for (int b = 0; b < nb; ++b) {
                 run += (double)blk_cost[b];
                 const int c = (int)h->h_chunk_unit.size();
-                if (c < vb::kChunks && run >= total * c / vb::kChunks && b + 1 < nb) h->h_chunk_unit.push_back(b + 1);
+                if (c < n_chunks_want && run >= total * c / n_chunks_want && b + 1 < nb) h->h_chunk_unit.push_back(b + 1);
             }
             h->h_chunk_unit.push_back(nb);
             h->n_chunks = (int32_t)h->h_chunk_unit.size() - 1;
