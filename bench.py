@@ -543,8 +543,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # (NCCL_DEBUG is left as the caller set it: with VERSION or above NCCL prints its banner on stdout next to rank 0's
+        # ONE JSON line, which is the last line)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

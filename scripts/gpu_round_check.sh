@@ -12,11 +12,11 @@ timeout 900 python bench.py > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TA
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_c2.json 2>/dev/null
 for w in c3 c4 c1 ln c5; do timeout 900 python bench.py --workload $w --no-cpu-baseline > gpurun_out/${TAG}_bench_$w.json 2> gpurun_out/${TAG}_bench_$w.err; done
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -c 40 --csv --log-file gpurun_out/${TAG}_c2_launches.csv \
+    -k regex:'sweep|prepare_kernel|sums_kernel|em_update|row_dot|forward_axpy' -c 24 --csv --log-file gpurun_out/${TAG}_c2_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > /dev/null 2>&1
 for w in c3 c4; do
   timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-      -c 40 --csv --log-file gpurun_out/${TAG}_${w}_launches.csv \
+      -k regex:'sweep|prepare_kernel|sums_kernel|em_update|row_dot|forward_axpy' -c 24 --csv --log-file gpurun_out/${TAG}_${w}_launches.csv \
       python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > /dev/null 2>&1
 done
 timeout 800 ncu --set full --import-source on --clock-control none -k regex:'sweep_fast' -s 3 -c 1 -o gpurun_out/${TAG}_c2_fast_full -f \

@@ -232,12 +232,19 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
     [[maybe_unused]] OutRings orr;
     orr.a_xown = sbase + FL.xown; orr.a_bsum = sbase + FL.bsum;
     orr.chain_panels = sm.prog + NAW + NWW + NCW; orr.out_rows = sm.prog + NAW + NWW + NCW + 1;
-    if (warp == FAST_PRODUCER_WARP) {
+#ifdef VB_CHAIN_SPLIT
+    // timing experiment: the second CTA of an SM (launch order: block ids >= SM count) swaps its chain / producer warps
+    const int swap = ((int)blockIdx.x >= VB_CHAIN_SPLIT) ? 1 : 0;
+    const int chain_warp = swap ? FAST_PRODUCER_WARP : FAST_CHAIN_WARP, producer_warp = swap ? FAST_CHAIN_WARP : FAST_PRODUCER_WARP;
+#else
+    constexpr int chain_warp = FAST_CHAIN_WARP, producer_warp = FAST_PRODUCER_WARP;
+#endif
+    if (warp == producer_warp) {
         producer_role<U>(p, smem, sm.rowmeta, sm.panelmeta, sm.full, sm.empty, r0, pan0, NP, lane,
                          reinterpret_cast<int*>(smem + FL.rowbase), reinterpret_cast<int4*>(smem + FL.panelmeta2));
     } else if (VER == 2 && warp == FAST_OUTPUT_WARP) {
         if constexpr (VER == 2) output_role<T, Model>(p, ma, sa, orr, r0, pan0, NP, lane, blk);
-    } else if (warp == FAST_CHAIN_WARP) {
+    } else if (warp == chain_warp) {
         if constexpr (VER == 2) chain_role2<T, Model, NAW, NCW>(p, ma, sa, sm, orr, r0, B, pan0, NP, lane);
         else chain_role<T, Model, NAW, NCW, NWW, T, INCR>(p, ma, sa, sm, r0, B, pan0, NP, lane);
     } else if (ai >= 0) {
