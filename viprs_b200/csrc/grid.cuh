@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(GRID_MAX_THREADS, 1) grid_sweep_kernel(const G
         // q registers.  float: pairs of adjacent GRID columns, q2[col][gp] = (q[col][2gp], q[col][2gp+1]), so that one
         // FFMA2 takes the decoded LD value as a 32-bit broadcast operand (R.F32), the two scaled deltas as a natural
         // 64-bit pair from the ring, and the accumulator pair -- measured 13% faster than pairing along the LD columns
-        // (scratch/fma_bench4.cu).  double: scalars.
+        // (the loop body in isolation: scripts/microbench/grid_loop_bench.cu).  double: scalars.
         using QT = typename std::conditional<F32, float2, double>::type;
         constexpr int QG = F32 ? GT / 2 : GT;
         QT qr[NVT][EPV][QG];

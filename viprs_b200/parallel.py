@@ -4,7 +4,7 @@ block, /root/reference/viprs/model/vi/e_step.hpp:389-392,421), so whole LD block
 only exchange per EM iteration is the small table of M-step / ELBO sums.
 
 Everything here is host logic (numpy + torch.distributed); it runs unchanged over NCCL on GPUs and over gloo on
-CPUs (tests/test_parallel_cpu.py).
+CPUs (the gloo world-2 / world-3 tests in tests/test_em_host.py).
 """
 import numpy as np
 
