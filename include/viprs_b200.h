@@ -108,7 +108,7 @@ int viprs_b200_ld_destroy(viprs_b200_ld_t* ld);
  * units; NULL = none) to every sweep.  The host drop-ins viprs_b200_cpp_e_step* always do this.
  *
  * LD blocks larger than 4096 SNPs (e.g. 10,240-SNP float64 blocks, or banded / windowed LD where a whole
- * chromosome is one block) are swept in 2048-row tiles: same per-SNP order, one launch per tile index plus
+ * chromosome is one block) are swept in 1024-row tiles: same per-SNP order, one launch per tile index plus
  * streaming products over the rectangles between tiles (viprs_b200_ld_info_t.n_phases launches).
  *
  * The reductions the M-step / ELBO need are produced by viprs_b200_sums_* (VIPRS_B200_S_* slots below).

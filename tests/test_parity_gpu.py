@@ -203,7 +203,7 @@ def test_device_path_and_ld_info(vb, oracle_built):
 
 def test_non_block_ld_is_tiled_not_refused(vb):
     """A single huge 'block' (banded genome-wide LD, no independent blocks at all) used to be refused; it is now swept
-    in 2048-row tiles (parity: tests/test_round2_gpu.py::test_banded_ld_is_swept_in_order).  Only the grid sweep,
+    in 1024-row tiles (parity: tests/test_round2_gpu.py::test_banded_ld_is_swept_in_order).  Only the grid sweep,
     which keeps a dense symmetric copy of every block, still refuses blocks larger than 4096 SNPs."""
     import torch
     M = 120000
@@ -212,7 +212,7 @@ def test_non_block_ld_is_tiled_not_refused(vb):
     ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     data = np.zeros(int(ip[-1]), np.int8)
     ld = vb.DeviceLD(data, ip, lb)
-    assert ld.n_blocks == 1 and ld.max_block == M and ld.n_phases == -(-M // 2048) and ld.n_units == ld.n_phases
+    assert ld.n_blocks == 1 and ld.max_block == M and ld.n_phases == -(-M // 1024) and ld.n_units == ld.n_phases
     G = 2
     z = lambda: torch.zeros(G, M, dtype=torch.float32, device="cuda").t()
     with pytest.raises(vb.ViprsB200Error) as ei:

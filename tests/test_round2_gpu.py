@@ -77,7 +77,7 @@ def test_tiled_blocks_match_oracle(vb, oracle_built, tn, un, blocks):
     hy = _hyper(rng, P["M"], T)
     ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
     assert ld.n_blocks == len(blocks) and ld.max_block == max(blocks)
-    assert ld.n_phases == -(-max(blocks) // 2048) and ld.n_units > ld.n_blocks and ld.ext_elems > 0
+    assert ld.n_phases == -(-max(blocks) // 1024) and ld.n_units > ld.n_blocks and ld.ext_elems > 0
     ld.destroy()
     ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
     got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
@@ -120,7 +120,7 @@ def test_banded_ld_is_swept_in_order(vb, oracle_built, tn, un):
     P = _banded(rng, 7001, 650, U, T)
     hy = _hyper(rng, P["M"], T)
     ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
-    assert ld.n_blocks == 1 and ld.n_phases == 4
+    assert ld.n_blocks == 1 and ld.n_phases == -(-7001 // 1024)
     ld.destroy()
     ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
     got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
@@ -224,13 +224,19 @@ def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
                 res["got4"] = _sweeps(vb.cpp_e_step, P, T, hy, n_sweeps)
             finally:
                 del os.environ["VIPRS_B200_LIMBS"]
+            # the incremental-q route (the reference's own q bookkeeping; what the host-state round trip and `e2e` run)
+            ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+            res["incr"] = _sweeps(lambda lb, ip, dat, *a: vb.cpp_e_step_resident(ld, *a[:-3], a[-3], False), P, T, hy, n_sweeps)
+            ld.destroy()
     rec = {}
     for k in ("eta", "var_gamma", "var_mu", "q"):
         rec[k] = {"floor_ref32_vs_ref64": relmax(res["ref_float32"][k], res["ref_float64"][k]),
                   "ours_vs_ref32": relmax(res["got3"][k], res["ref_float32"][k]),
                   "ours_vs_ref64": relmax(res["got3"][k], res["ref_float64"][k]),
                   "ours_limbs4_vs_ref64": relmax(res["got4"][k], res["ref_float64"][k]),
-                  "limbs3_vs_limbs4": relmax(res["got3"][k], res["got4"][k])}
+                  "limbs3_vs_limbs4": relmax(res["got3"][k], res["got4"][k]),
+                  "incremental_vs_ref32": relmax(res["incr"][k], res["ref_float32"][k]),
+                  "incremental_vs_ref64": relmax(res["incr"][k], res["ref_float64"][k])}
     _record(f"c2_block_int8_{n_sweeps}_sweeps", rec)
     print(json.dumps(rec))
     for k in ("eta", "var_gamma"):
@@ -240,6 +246,7 @@ def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
         assert r["ours_vs_ref32"] <= 1e-4 or r["ours_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
         # the 21-bit fixed-point representation adds nothing visible next to float32 rounding
         assert r["limbs3_vs_limbs4"] <= max(1e-4, 2 * r["floor_ref32_vs_ref64"]), (k, r)
+        assert r["incremental_vs_ref32"] <= 1e-4 or r["incremental_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
 
 
 @pytest.mark.parametrize("n_sweeps", [10, 50])

@@ -155,12 +155,13 @@ static int launch_backward(const viprs_b200_ld* ld, const T* x, T* q, T dq, cuda
 // out[k] += scale * sum_j R_jk x[j] over `n_items` items (see forward_axpy_kernel); max_cols: widest item
 template <typename T, typename U>
 static int launch_forward(const int4* items, int n_items, int max_cols, const void* rows, const int64_t* prow,
-                          const int32_t* pcs, const T* x, T* out, T scale, cudaStream_t st) {
+                          const int32_t* pcs, const T* x, T* out, T scale, cudaStream_t st, int max_rows = FWD_MAX_ROWS) {
     if (n_items <= 0 || max_cols <= 0) return VIPRS_B200_OK;
     constexpr int EPV = LdTraits<U>::EPV;
     dim3 grid((max_cols + FWD_THREADS * EPV - 1) / (FWD_THREADS * EPV), n_items);
-    forward_axpy_kernel<T, U><<<grid, FWD_THREADS, 0, st>>>(items, reinterpret_cast<const unsigned char*>(rows), prow, pcs,
-                                                           x, out, scale);
+    // an item's rows are those of one sweep unit: at most FWD_MAX_ROWS (= kTileLimit)
+    forward_axpy_kernel<T, U><<<grid, FWD_THREADS, forward_smem_bytes(max_rows, (int)sizeof(T)), st>>>(
+        items, reinterpret_cast<const unsigned char*>(rows), prow, pcs, x, out, scale);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
 }
@@ -199,7 +200,7 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
         const int i0 = ld->h_ext_phase_ptr[ph], i1 = ld->h_ext_phase_ptr[ph + 1];
         if (rc == 0 && i1 > i0)
             rc = launch_forward<T, U>(ld->d_items_ext + i0, i1 - i0, ld->h_items_cols[ph], ld->d_ext, ld->d_erow, ld->d_ecs,
-                                      sa.eta, fext, T(1), st);
+                                      sa.eta, fext, T(1), st, ld->max_block);
     }
     return rc;
 }

@@ -244,7 +244,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
         // would fit one unit)
         int tile_limit = vb::kTileLimit, tile_rows = vb::kTileRows;
         if (const char* e = getenv("VIPRS_B200_TILE_LIMIT")) { const int v = atoi(e); if (v >= 64 && v <= vb::kTileLimit) tile_limit = v; }
-        if (const char* e = getenv("VIPRS_B200_TILE_ROWS")) { const int v = atoi(e); if (v >= 64 && v <= vb::kTileRows && v % 16 == 0) tile_rows = v; }
+        if (const char* e = getenv("VIPRS_B200_TILE_ROWS")) { const int v = atoi(e); if (v >= 64 && v <= 2048 && v % 16 == 0) tile_rows = v; }
         std::vector<int32_t> blk_row, unit_phase;
         int32_t max_ld_block = 0, n_phases = 1;
         for (int b = 0; b < nlb; ++b) {

@@ -1225,6 +1225,11 @@ __global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __rest
 // sums in registers.  Used for the forward-external accumulator of tiled LD blocks and for q offsets.
 constexpr int FWD_THREADS = 128;
 constexpr int FWD_MAX_ROWS = 4096;
+constexpr int FWD_SLAB = 256;                 // rows whose offsets / first columns are staged at a time
+// dynamic shared memory: the item's x values only (rows * sizeof(T)); a float64 tile of 2048 rows takes 16 KB, so a
+// dozen CTAs share an SM and keep enough 16-byte loads in flight for HBM (a static 44 KB block held it to five:
+// 1.06 ms for a 2.45 GB phase of the C5 workload)
+inline size_t forward_smem_bytes(int max_rows, int tsize) { return (size_t)max_rows * (size_t)tsize; }
 template <typename T, typename U>
 __global__ void __launch_bounds__(FWD_THREADS) forward_axpy_kernel(const int4* __restrict__ items,
                                                                   const unsigned char* __restrict__ packed,
@@ -1232,9 +1237,10 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_axpy_kernel(const int4* _
                                                                   const int32_t* __restrict__ pcs,
                                                                   const T* __restrict__ x, T* __restrict__ out, T scale) {
     constexpr int EPV = LdTraits<U>::EPV;
-    __shared__ T xs[FWD_MAX_ROWS];
-    __shared__ int64_t ro[FWD_MAX_ROWS / 4 + 1];       // row offsets / first columns of a 1024-row slab
-    __shared__ int32_t rc[FWD_MAX_ROWS / 4];
+    extern __shared__ __align__(16) unsigned char fwd_smem[];
+    T* xs = reinterpret_cast<T*>(fwd_smem);
+    __shared__ int64_t ro[FWD_SLAB + 1];               // row offsets / first columns of a slab of rows
+    __shared__ int32_t rc[FWD_SLAB];
     const int4 it = items[blockIdx.y];
     const int row0 = it.x, row1 = it.y, col0 = it.z, col1 = it.w;
     const int v = blockIdx.x * FWD_THREADS + threadIdx.x;
@@ -1244,15 +1250,14 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_axpy_kernel(const int4* _
     T acc[EPV];
 #pragma unroll
     for (int e = 0; e < EPV; ++e) acc[e] = T(0);
-    constexpr int SLAB = FWD_MAX_ROWS / 4;
-    for (int s0 = row0; s0 < row1; s0 += SLAB) {
-        const int ns = min(SLAB, row1 - s0);
+    for (int s0 = row0; s0 < row1; s0 += FWD_SLAB) {
+        const int ns = min(FWD_SLAB, row1 - s0);
         __syncthreads();
         for (int i = threadIdx.x; i <= ns; i += FWD_THREADS) ro[i] = prow[s0 + i];
         for (int i = threadIdx.x; i < ns; i += FWD_THREADS) rc[i] = pcs[s0 + i];
         __syncthreads();
         if (col < col1) {
-#pragma unroll 4
+#pragma unroll 8
             for (int i = 0; i < ns; ++i) {
                 const int64_t o = ro[i];
                 const int rel = col - rc[i];

@@ -73,7 +73,7 @@ class DeviceLD:
         self.smem_bytes = info.smem_bytes
         self.ring_stages = info.ring_stages
         self.ctas_per_sm = info.ctas_per_sm
-        self.n_units = info.n_units            # sweep units (LD blocks, or 2048-row tiles of blocks > 4096 rows)
+        self.n_units = info.n_units            # sweep units (LD blocks, or 1024-row tiles of blocks > 4096 rows)
         self.n_phases = info.n_phases          # sweep launches per E-step
         self.ext_elems = info.ext_elems
         self.elem_size = {0: 1, 1: 2, 2: 4, 3: 8}[info.ld_dtype]
