@@ -158,12 +158,29 @@ static int launch_forward(const int4* items, int n_items, int max_cols, const vo
                           const int32_t* pcs, const T* x, T* out, T scale, cudaStream_t st, int max_rows = FWD_MAX_ROWS) {
     if (n_items <= 0 || max_cols <= 0) return VIPRS_B200_OK;
     constexpr int EPV = LdTraits<U>::EPV;
-    dim3 grid((max_cols + FWD_THREADS * EPV - 1) / (FWD_THREADS * EPV), n_items);
+    dim3 grid((max_cols + FWD_THREADS * FWD_VPT * EPV - 1) / (FWD_THREADS * FWD_VPT * EPV), n_items);
     // an item's rows are those of one sweep unit: at most FWD_MAX_ROWS (= kTileLimit)
     forward_axpy_kernel<T, U><<<grid, FWD_THREADS, forward_smem_bytes(max_rows, (int)sizeof(T)), st>>>(
         items, reinterpret_cast<const unsigned char*>(rows), prow, pcs, x, out, scale);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? VIPRS_B200_OK : (int)e;
+}
+
+// side stream + events of a tiled LD handle, created on first use
+static bool side_stream_ready(const viprs_b200_ld* ld) {
+    if (ld->side_stream) return true;
+    if (cudaStreamCreateWithFlags(&ld->side_stream, cudaStreamNonBlocking) != cudaSuccess) { ld->side_stream = nullptr; return false; }
+    ld->side_events.assign(ld->n_phases + 1, nullptr);
+    for (auto& ev : ld->side_events) {
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            for (cudaEvent_t x : ld->side_events) if (x) cudaEventDestroy(x);
+            ld->side_events.clear();
+            cudaStreamDestroy(ld->side_stream);
+            ld->side_stream = nullptr;
+            return false;
+        }
+    }
+    return true;
 }
 
 template <typename T>
@@ -193,9 +210,32 @@ static int launch_sweep(const viprs_b200_ld* ld, const typename Model::Args& ma,
     scale_copy_kernel<T><<<(M + 255) / 256, 256, 0, st>>>(M, q_offset, T(1) / dq, fext);
     cudaError_t e = cudaMemsetAsync(bext, 0, sizeof(T) * (size_t)M, st);
     if (e != cudaSuccess) return (int)e;
-    int rc = launch_row_dots<T, U>(ld->d_items_bwd_ext, ld->n_items_bwd_ext, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1), st);
+    // The backward-external dots of tile p only have to be complete before launch p, and the sequential launches keep
+    // one CTA per LD block busy (73 of 148 SMs at the C5 shape): the dots run phase by phase on a side stream, next to
+    // the sweeps and forward products of the earlier tiles (they read eta of later tiles only, which those do not
+    // write).  The side stream is forked from and joined back into `st` with events, so the whole sweep stays
+    // capturable in a CUDA graph.
+    int rc = VIPRS_B200_OK;
+    const bool side = ld->n_phases > 1 && env_int("VIPRS_B200_NO_SIDE_STREAM", 0) == 0 && side_stream_ready(ld);
+    if (side) {
+        e = cudaEventRecord(ld->side_events[0], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ld->side_stream, ld->side_events[0], 0);
+        for (int ph = 0; ph < ld->n_phases && rc == 0 && e == cudaSuccess; ++ph) {
+            const int i0 = ld->h_bwd_ext_phase_ptr[ph], i1 = ld->h_bwd_ext_phase_ptr[ph + 1];
+            rc = launch_row_dots<T, U>(ld->d_items_bwd_ext + i0, i1 - i0, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1),
+                                       ld->side_stream);
+            if (rc == 0) e = cudaEventRecord(ld->side_events[ph + 1], ld->side_stream);
+        }
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        rc = launch_row_dots<T, U>(ld->d_items_bwd_ext, ld->n_items_bwd_ext, ld->d_ext, ld->d_erow, ld->d_ecs, sa.eta, bext, T(1), st);
+    }
     sa.fext = fext; sa.bext = bext; sa.fscale = T(1);
     for (int ph = 0; ph < ld->n_phases && rc == 0; ++ph) {
+        if (side) {
+            e = cudaStreamWaitEvent(st, ld->side_events[ph + 1], 0);
+            if (e != cudaSuccess) return (int)e;
+        }
         rc = launch_phase<T, U, Model>(ld, ph, ma, sa, st);
         const int i0 = ld->h_ext_phase_ptr[ph], i1 = ld->h_ext_phase_ptr[ph + 1];
         if (rc == 0 && i1 > i0)

@@ -384,6 +384,27 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
                 if (erow[je] > erow[j]) items_bwd_ext.push_back(make_int4(j, je, r1, unit_ext_end[b]));
             }
         }
+        // the ext row-dot items grouped by the phase of the unit that owns their rows: the dots of tile p + 1 only have to
+        // be there before launch p + 1, so they can run next to the sweep of tile p (launch.cuh: launch_sweep)
+        {
+            std::vector<int32_t> item_phase(items_bwd_ext.size());
+            size_t k = 0;
+            for (int b = 0; b < nb; ++b) {
+                const int r0 = blk_row[b], r1 = blk_row[b + 1];
+                for (int j = r0; j < r1; j += 64) {
+                    const int je = std::min(j + 64, r1);
+                    if (erow[je] > erow[j]) item_phase[k++] = unit_phase[b];
+                }
+            }
+            std::vector<int32_t> perm(items_bwd_ext.size());
+            std::iota(perm.begin(), perm.end(), 0);
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int c) { return item_phase[a] < item_phase[c]; });
+            std::vector<int4> sorted(items_bwd_ext.size());
+            h->h_bwd_ext_phase_ptr.assign(n_phases + 1, 0);
+            for (size_t i = 0; i < perm.size(); ++i) { sorted[i] = items_bwd_ext[perm[i]]; h->h_bwd_ext_phase_ptr[item_phase[perm[i]] + 1]++; }
+            for (int p = 0; p < n_phases; ++p) h->h_bwd_ext_phase_ptr[p + 1] += h->h_bwd_ext_phase_ptr[p];
+            items_bwd_ext.swap(sorted);
+        }
         h->n_items_bwd = (int32_t)items_bwd.size();
         h->n_items_bwd_ext = (int32_t)items_bwd_ext.size();
         // row chunks of about equal sweep cost (single-phase LD with enough units)
@@ -572,6 +593,7 @@ extern "C" int viprs_b200_ld_destroy(viprs_b200_ld_t* h) {
     cudaFree(h->d_ext); cudaFree(h->d_erow); cudaFree(h->d_ecs); cudaFree(h->d_items_diag); cudaFree(h->d_items_ext); cudaFree(h->d_items_bwd); cudaFree(h->d_items_bwd_ext);
     cudaFree(h->d_fext); cudaFree(h->d_bext); cudaFree(h->d_host_ws); cudaFree(h->d_unit_partial);
     cudaFree(h->d_packed); cudaFree(h->d_prow); cudaFree(h->d_pcs); cudaFree(h->d_blk_row);
+    if (h->side_stream) { cudaStreamDestroy(h->side_stream); for (cudaEvent_t e : h->side_events) cudaEventDestroy(e); }
     cudaFree(h->d_blk_panel); cudaFree(h->d_panel_row); cudaFree(h->d_panel_need); cudaFree(h->d_blk_order); cudaFree(h->d_chunk_order);
     delete h;
     return VIPRS_B200_OK;

@@ -61,6 +61,9 @@ struct viprs_b200_ld {
     int4* d_items_bwd_ext = nullptr;   // ... and of every unit's ext rows
     int32_t n_items_bwd = 0, n_items_bwd_ext = 0;
     std::vector<int32_t> h_ext_phase_ptr;   // [n_phases+1] slice of d_items_ext belonging to phase p
+    std::vector<int32_t> h_bwd_ext_phase_ptr;   // [n_phases+1] slice of d_items_bwd_ext (sorted by phase)
+    mutable cudaStream_t side_stream = nullptr;     // the backward-external dots of later tiles run here, next to the sweeps
+    mutable std::vector<cudaEvent_t> side_events;   // [n_phases + 1]: fork + one per phase
     std::vector<int32_t> h_items_cols;      // max columns of an item per phase / overall (grid sizing)
     void* d_unit_partial = nullptr;   // [n_blocks][VIPRS_B200_NSUMS] doubles: per-unit sums of the fused sweep
     mutable void* d_host_ws = nullptr;   // staging of HOST state arrays (viprs_b200_cpp_e_step_resident), grown on demand

@@ -1223,7 +1223,14 @@ __global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __rest
 // chunk c owns LD vector c * FWD_THREADS + t of the item's column range (the row layouts of ld.cu are aligned to
 // 16 bytes relative to col0), walks the rows in order (fixed summation order: deterministic) and keeps its EPV
 // sums in registers.  Used for the forward-external accumulator of tiled LD blocks and for q offsets.
-constexpr int FWD_THREADS = 128;
+#ifndef VB_FWD_THREADS
+#define VB_FWD_THREADS 128
+#endif
+#ifndef VB_FWD_VPT
+#define VB_FWD_VPT 1
+#endif
+constexpr int FWD_THREADS = VB_FWD_THREADS;
+constexpr int FWD_VPT = VB_FWD_VPT;           // LD vectors per thread: a CTA covers FWD_THREADS * FWD_VPT * 16 contiguous bytes of every row
 constexpr int FWD_MAX_ROWS = 4096;
 constexpr int FWD_SLAB = 256;                 // rows whose offsets / first columns are staged at a time
 // dynamic shared memory: the item's x values only (rows * sizeof(T)); a float64 tile of 2048 rows takes 16 KB, so a
@@ -1243,35 +1250,47 @@ __global__ void __launch_bounds__(FWD_THREADS) forward_axpy_kernel(const int4* _
     __shared__ int32_t rc[FWD_SLAB];
     const int4 it = items[blockIdx.y];
     const int row0 = it.x, row1 = it.y, col0 = it.z, col1 = it.w;
-    const int v = blockIdx.x * FWD_THREADS + threadIdx.x;
-    const int col = col0 + v * EPV;
-    if (col0 + (int)blockIdx.x * FWD_THREADS * EPV >= col1) return;          // whole CTA beyond the item (uniform)
-    for (int i = threadIdx.x; i < row1 - row0; i += FWD_THREADS) xs[i] = x[row0 + i];
-    T acc[EPV];
+    const int cta_col0 = col0 + (int)blockIdx.x * FWD_THREADS * FWD_VPT * EPV;
+    if (cta_col0 >= col1) return;                                            // whole CTA beyond the item (uniform)
+    int col[FWD_VPT];
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) acc[e] = T(0);
+    for (int k = 0; k < FWD_VPT; ++k) col[k] = cta_col0 + (k * FWD_THREADS + (int)threadIdx.x) * EPV;
+    for (int i = threadIdx.x; i < row1 - row0; i += FWD_THREADS) xs[i] = x[row0 + i];
+    T acc[FWD_VPT][EPV];
+#pragma unroll
+    for (int k = 0; k < FWD_VPT; ++k)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[k][e] = T(0);
     for (int s0 = row0; s0 < row1; s0 += FWD_SLAB) {
         const int ns = min(FWD_SLAB, row1 - s0);
         __syncthreads();
         for (int i = threadIdx.x; i <= ns; i += FWD_THREADS) ro[i] = prow[s0 + i];
         for (int i = threadIdx.x; i < ns; i += FWD_THREADS) rc[i] = pcs[s0 + i];
         __syncthreads();
-        if (col < col1) {
-#pragma unroll 8
+        if (col[0] < col1) {
+#pragma unroll 8 / FWD_VPT
             for (int i = 0; i < ns; ++i) {
                 const int64_t o = ro[i];
-                const int rel = col - rc[i];
-                if (rel >= 0 && rel < (int)(ro[i + 1] - o)) {
-                    const uint4 c = __ldg(reinterpret_cast<const uint4*>(packed + (o + rel) * (int64_t)sizeof(U)));
-                    VecOps<T, U>::axpy(c, xs[s0 - row0 + i], acc);
+                const int len = (int)(ro[i + 1] - o), c0 = rc[i];
+                const T xv = xs[s0 - row0 + i];
+#pragma unroll
+                for (int k = 0; k < FWD_VPT; ++k) {
+                    const int rel = col[k] - c0;
+                    if (rel >= 0 && rel < len) {
+                        const uint4 c = __ldg(reinterpret_cast<const uint4*>(packed + (o + rel) * (int64_t)sizeof(U)));
+                        VecOps<T, U>::axpy(c, xv, acc[k]);
+                    }
                 }
             }
         }
     }
-    if (col < col1) {
 #pragma unroll
-        for (int e = 0; e < EPV; ++e)
-            if (col + e < col1) out[col + e] = fma_t(scale, acc[e], out[col + e]);
+    for (int k = 0; k < FWD_VPT; ++k) {
+        if (col[k] < col1) {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                if (col[k] + e < col1) out[col[k] + e] = fma_t(scale, acc[k][e], out[col[k] + e]);
+        }
     }
 }
 
