@@ -271,3 +271,41 @@ def test_model_on_bigger_blocks_against_oracle(vb, oracle_built):
     for c in data:
         assert relmax(m.eta[c].cpu().numpy(), o.eta[c]) <= 1e-4
         assert relmax(m.q[c].cpu().numpy(), o.q[c]) <= 1e-4
+
+
+@pytest.mark.parametrize("pathwise", [False, True])
+def test_viprsgrid_lambda_min_column_matches_oracle(vb, oracle_built, pathwise):
+    """A grid with a lambda_min column (the reference's set_fixed_params sets self.lambda_min for every grid point,
+    VIPRS.py:855-870 / VIPRSGrid.py:190-196): every column against an independent fit of the numpy restatement with that
+    lambda_min (advisor finding, round 1: model 0 of a pathwise fit used the constructor's lambda_min)."""
+    from oracle import cpu as ocpu
+    from viprs_b200.model import VIPRSGrid
+    d, ch = load_golden("viprs_f32_i8.npz")
+    keys = sorted(ch)
+    data = {c: ch[c] for c in keys}
+    grid = [{"pi": 0.02, "sigma_epsilon": 0.8, "lambda_min": lm} for lm in (0.3, 0.0, 0.1)]
+    m = VIPRSGrid(data=data, grid=grid, float_precision="float32")
+    n_it = 5
+    if pathwise:
+        m.fit(pathwise=True, max_iter=n_it, min_iter=100)
+    else:
+        m.fit(pathwise=False, max_iter=n_it, min_iter=100)
+    Oracle = _oracle_grid_column(ocpu) if not pathwise else ocpu.OracleVIPRS
+    o = None
+    for g, rec in enumerate(grid):
+        fix = {k: v for k, v in rec.items() if k != "lambda_min"}
+        if not pathwise or o is None:
+            o = Oracle({c: (ch[c]["ld_data"], ch[c]["ld_indptr"], ch[c]["ld_left_bound"]) for c in keys},
+                       {c: ch[c]["std_beta"] for c in keys}, {c: ch[c]["n_per_snp"] for c in keys},
+                       fix_params=fix, lambda_min=rec["lambda_min"], float_precision="float32", dequantize_on_the_fly=True)
+            o.run(n_it, {})
+        else:
+            # the reference's pathwise loop: fix the next grid point and continue from the current state
+            o.lambda_min = rec["lambda_min"]
+            o.fix_params.update(fix)
+            o.sigma_epsilon, o.pi = fix["sigma_epsilon"], fix["pi"]
+            for _ in range(n_it):
+                o.e_step(); o.m_step()
+        for c in keys:
+            assert relmax(m.var_gamma[c][:, g].cpu().numpy(), o.var_gamma[c]) <= 2e-4, (g, c, pathwise)
+            assert relmax(m.eta[c][:, g].cpu().numpy(), o.eta[c]) <= 2e-4, (g, c, pathwise)
