@@ -64,3 +64,10 @@ for w in CW:
     print(f"  C{w}: groups " + " | ".join(f"{perwarp(w, 4, 6, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))) +
           "  publish " + " | ".join(f"{perwarp(w, 6, 5, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))
 print("chain period/panel        " + "".join(f"{(CD[q[i + 1] - 1] - CD[q[i]]) / (q[i + 1] - 1 - q[i]):10.0f}" for i in range(4)))
+# fine-grained A row-group trace (builds with -DVB_TRACE2): A warp index 3, second row group of every panel
+T = [series(10, e) for e in range(6)]
+if T[0]:
+    names = ["row-group top -> row bases loaded", "-> last tile's LDS.128 issued", "-> its data landed", "-> IDP.4A done", "-> REDUX + selects done"]
+    print("A (index 3) second row group, by block half (cycles):")
+    for i, nm in enumerate(names):
+        print(f"  {nm:36s}" + " | ".join(f"{avg(T[i], T[i + 1], a, b):7.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))

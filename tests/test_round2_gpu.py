@@ -564,11 +564,31 @@ def test_incremental_sweep_unsupported_for_float64(vb):
     ld.destroy()
 
 
+_PINNED_KEEP = []
+
+
+def _pinned(a, shift=0):
+    """A page-locked (torch pin_memory) copy of `a` as a numpy array; shift > 0: a view that starts `shift` elements into
+    the pinned allocation (its base is then not 16-byte aligned)."""
+    import torch
+    a = np.ascontiguousarray(a)
+    buf = torch.empty(a.size + shift, dtype=torch.from_numpy(a).dtype).pin_memory()
+    _PINNED_KEEP.append(buf)
+    v = buf.numpy()[shift:shift + a.size].reshape(a.shape)
+    v[...] = a
+    return v
+
+
 @pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f32", "f32"), ("f64", "f64")])
 @pytest.mark.parametrize("q_in,vouch", [("zero", False), ("garbage", False)])
-def test_resident_host_state_matches_oracle(vb, oracle_built, tn, un, q_in, vouch):
+@pytest.mark.parametrize("mem", ["pageable", "pinned", "pinned_shifted"])
+def test_resident_host_state_matches_oracle(vb, oracle_built, tn, un, q_in, vouch, mem):
     """viprs_b200_cpp_e_step_resident: HOST state arrays on a resident LD, 3 calls.  float32: incremental sweep in row
-    chunks on internal streams; float64: q offset + one-pass sweep."""
+    chunks on internal streams; float64: q offset + one-pass sweep.  Page-locked arrays (what bench.py's e2e leg passes)
+    make the chunk copies truly asynchronous; chunk offsets that are not multiples of 16 bytes and array bases that are
+    not 16-byte aligned must not matter."""
+    if mem != "pageable" and (tn != "f32" or q_in == "zero"):
+        pytest.skip("page-locked variants: the chunked float32 route, one start")
     T = np.float32 if tn == "f32" else np.float64
     U = {"i8": np.int8, "f32": np.float32, "f64": np.float64}[un]
     rng = np.random.default_rng(22)
@@ -578,10 +598,15 @@ def test_resident_host_state_matches_oracle(vb, oracle_built, tn, un, q_in, vouc
     ref = _sweeps(oracle_built.e_step, P, T, hy, 3, _incr_start(np.random.default_rng(9), M, T, q_in))
     st = _incr_start(np.random.default_rng(9), M, T, q_in)
     u_logs, shvt, mm, _ = hy
+    u_logs, shvt, mm = (np.ascontiguousarray(a) for a in (u_logs, shvt, mm))
+    if mem != "pageable":
+        st = {k: _pinned(v, 1 if (mem == "pinned_shifted" and k == "eta") else 0) for k, v in st.items()}
+        P = dict(P, beta=_pinned(P["beta"]))
+        u_logs, shvt, mm = _pinned(u_logs), _pinned(shvt, 3 if mem == "pinned_shifted" else 0), _pinned(mm)
     ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
     for _ in range(3):
         vb.cpp_e_step_resident(ld, P["beta"], st["var_gamma"], st["var_mu"], st["eta"], st["q"], st["eta_diff"],
-                               np.ascontiguousarray(u_logs), np.ascontiguousarray(shvt), np.ascontiguousarray(mm), P["dq"], vouch)
+                               u_logs, shvt, mm, P["dq"], vouch)
     tol = 1e-4 if T == np.float32 else 1e-10
     for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
         assert relmax(st[k], ref[k]) <= tol, (k, relmax(st[k], ref[k]))
@@ -589,8 +614,10 @@ def test_resident_host_state_matches_oracle(vb, oracle_built, tn, un, q_in, vouc
 
 
 @pytest.mark.parametrize("K", [1, 3, 4])
-def test_resident_mixture_host_state_matches_oracle(vb, oracle_built, K):
-    """viprs_b200_cpp_e_step_mixture_resident (int16 LD, float32): chunked incremental mixture sweep, 3 calls."""
+@pytest.mark.parametrize("mem", ["pageable", "pinned"])
+def test_resident_mixture_host_state_matches_oracle(vb, oracle_built, K, mem):
+    """viprs_b200_cpp_e_step_mixture_resident (int16 LD, float32): chunked incremental mixture sweep, 3 calls, pageable
+    and page-locked host arrays."""
     T = np.float32
     rng = np.random.default_rng(23)
     P = make_block_ld(rng, _INCR_BLOCKS, np.int16, T)
@@ -605,6 +632,10 @@ def test_resident_mixture_host_state_matches_oracle(vb, oracle_built, K):
     lnp = np.full(M, np.log(1 - pis.sum()), T)
     ref = _incr_start(np.random.default_rng(9), M, T, "garbage", K)
     got = _incr_start(np.random.default_rng(9), M, T, "garbage", K)
+    if mem == "pinned":
+        got = {k: _pinned(v) for k, v in got.items()}
+        P = dict(P, beta=_pinned(P["beta"]))
+        lnp, u_logs, shvt, mm = _pinned(lnp), _pinned(u_logs), _pinned(shvt), _pinned(mm)
     ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
     for _ in range(3):
         oracle_built.e_step_mixture(P["lb"], P["indptr"], P["data"], P["beta"], ref["var_gamma"], ref["var_mu"], ref["eta"],

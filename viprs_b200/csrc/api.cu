@@ -88,6 +88,13 @@ int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, c
         const int nch = ld->n_chunks > 0 ? ld->n_chunks : 1;
         HostStreams* hs = host_streams(nch);
         if (hs) {
+            // VIPRS_B200_E2E_TIMING=1 (debug): device timeline of the call, per chunk, printed to stderr
+            const bool timing = getenv("VIPRS_B200_E2E_TIMING") != nullptr;
+            cudaEvent_t tev[1 + 3 * HostStreams::kMax] = {};
+            if (timing) {
+                for (int i = 0; i < 1 + 3 * nch; ++i) cudaEventCreate(&tev[i]);
+                cudaEventRecord(tev[0], st);
+            }
             // all chunks wait for whatever the caller queued on `st`
             if (e == cudaSuccess) e = cudaEventRecord(hs->fork, st);
             bool unsupported = false;
@@ -97,6 +104,8 @@ int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, c
                 const size_t r0 = ld->n_chunks > 0 ? (size_t)ld->h_chunk_row[c] : 0;
                 const size_t r1 = ld->n_chunks > 0 ? (size_t)ld->h_chunk_row[c + 1] : (size_t)M;
                 const size_t o1 = r0 * ts, b1 = (r1 - r0) * ts, ok_ = o1 * kk, bk = b1 * kk;
+                // (moving the arrays with kernels over mapped page-locked memory instead of DMA copies was measured: same
+                // PCIe rate, more contention with the sweeps -- 2.9 vs 2.5 ms per call; scripts/microbench/h2d_bench.cu)
                 auto upc = [&](unsigned char* dst, const void* src, size_t off, size_t n) {
                     if (e == cudaSuccess && src && n)
                         e = cudaMemcpyAsync(dst + off, reinterpret_cast<const unsigned char*>(src) + off, n, cudaMemcpyHostToDevice, sc);
@@ -106,24 +115,37 @@ int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, c
                 upc(d_g, var_gamma, ok_, bk); upc(d_mu, var_mu, ok_, bk); upc(d_ul, u_logs, ok_, bk); upc(d_sv, shvt, ok_, bk);
                 upc(d_mm, mu_mult, ok_, bk);
                 if (e != cudaSuccess) break;
+                if (timing) cudaEventRecord(tev[1 + 3 * c], sc);
                 const int chunk = ld->n_chunks > 0 ? c : -1;
                 rc = K > 0 ? vb::incr_mix_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_lnp,
                                               (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc)
                            : vb::incr_slab_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
                                                (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc);
                 if (rc == VIPRS_B200_EUNSUPPORTED && c == 0) { unsupported = true; rc = 0; break; }
+                if (timing) cudaEventRecord(tev[2 + 3 * c], sc);
                 auto downc = [&](void* dst, unsigned char* src, size_t off, size_t n) {
                     if (e == cudaSuccess && rc == 0 && n)
                         e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(dst) + off, src + off, n, cudaMemcpyDeviceToHost, sc);
                 };
                 downc(var_gamma, d_g, ok_, bk); downc(var_mu, d_mu, ok_, bk); downc(eta, d_eta, o1, b1); downc(q, d_q, o1, b1);
                 downc(eta_diff, d_diff, o1, b1);
+                if (timing) cudaEventRecord(tev[3 + 3 * c], sc);
                 if (e == cudaSuccess) e = cudaEventRecord(hs->join[c], sc);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hs->join[c], 0);
             }
             if (!unsupported) {
                 cudaError_t e2 = cudaStreamSynchronize(st);
                 for (int c = 0; c < nch; ++c) cudaStreamSynchronize(hs->s[c]);
+                if (timing) {
+                    for (int c = 0; c < nch; ++c) {
+                        float a = 0, b = 0, d2 = 0;
+                        cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * c]); cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * c]);
+                        cudaEventElapsedTime(&d2, tev[0], tev[3 + 3 * c]);
+                        fprintf(stderr, "[viprs_b200 e2e] chunk %d: inputs on device %.3f ms, sweep + q pass done %.3f ms, outputs on host %.3f ms\n",
+                                c, a, b, d2);
+                    }
+                    for (int i = 0; i < 1 + 3 * nch; ++i) cudaEventDestroy(tev[i]);
+                }
                 if (e == cudaSuccess) e = e2;
                 if (rc) return rc;
                 return e == cudaSuccess ? VIPRS_B200_OK : (int)e;

@@ -24,6 +24,8 @@ static int make_plan(const viprs_b200_ld* ld, int tsize, SweepPlan& p, RingGeome
     p.panel_row = ld->d_panel_row; p.blk_order = ld->d_blk_order; p.panel_need = ld->d_panel_need;
     p.n_blocks = ld->n_blocks; p.stage_bytes = ld->stage_bytes; p.nst = g.nst; p.bpad = state_pad(ld->max_block);
     p.l2_ahead = env_int("VIPRS_B200_L2_AHEAD", 0);
+    p.n_sm = ld->n_sm > 0 ? ld->n_sm : 148;
+    p.smsp_rot = env_int("VIPRS_B200_SMSP_ROT", 1);
     p.trace = nullptr;
     p.L = make_layout(p.bpad, tsize, ld->stage_bytes, g.nst);
     return g.nst == 0 ? VIPRS_B200_EBLOCK_TOO_LARGE : VIPRS_B200_OK;

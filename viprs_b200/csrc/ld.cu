@@ -301,6 +301,7 @@ extern "C" int viprs_b200_ld_create(viprs_b200_ld_t** out, int32_t M, const int3
 
         CUDA_TRY(cudaGetDevice(&h->device));
         CUDA_TRY(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device));
         h->M = M; h->ld_dtype = ld_dtype; h->esize = esize; h->epv = epv; h->nnz = nnz;
         h->packed_elems = off; h->ext_elems = eoff; h->n_blocks = nb; h->max_block = max_block; h->max_row_bytes = max_row_bytes;
         h->n_ld_blocks = nlb; h->max_ld_block = max_ld_block; h->n_phases = n_phases;

@@ -21,6 +21,7 @@ struct viprs_b200_ld {
     int32_t stage_bytes = 0;
     int device = 0;
     int smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int n_sm = 0;               // cudaDevAttrMultiProcessorCount
 
     // device arrays
     void* d_packed = nullptr;      // [packed_elems] LD entries (biased integer codes), rows 16B-aligned

@@ -76,6 +76,8 @@ struct SweepPlan {                 // what ld.cu prepared (device pointers) + th
     int nst;
     int bpad;
     int l2_ahead;                  // panels of L2 prefetch distance beyond the ring
+    int n_sm;                      // SMs of the device (the register-resident kernel: CTA b and CTA b + n_sm share an SM)
+    int smsp_rot;                  // register-resident kernel: placement of the bulk warps' tile shares on the SM sub-partitions
     unsigned long long* trace;     // debug timeline of CTA 0 (VIPRS_B200_TRACE), else null
     SmemLayout L;
 };
@@ -1174,6 +1176,15 @@ __global__ void backward_dot_kernel(int M, const unsigned char* __restrict__ pac
 constexpr int BWD_ROWS = 64;
 constexpr int BWD_COLS = 4096;
 constexpr int BWD_THREADS = 256;
+#ifndef VB_BWD_RG
+#define VB_BWD_RG 4
+#endif
+// rows a warp of row_dot_kernel handles together: 4 where a 16-byte LD vector needs more than 16 bytes of x from shared
+// memory (integer LD codes, float LD with float64 state), 1 where it needs 16 (measured on the float64 C5 workload: the
+// grouped form is slower there, 14.8 vs 13.5 ms per sweep)
+template <typename T, typename U> constexpr int bwd_rows_per_warp() {
+    return (int)sizeof(T) * LdTraits<U>::EPV > 16 ? VB_BWD_RG : 1;
+}
 template <typename T, typename U>
 __global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __restrict__ items,
                                                              const unsigned char* __restrict__ packed,
@@ -1181,6 +1192,7 @@ __global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __rest
                                                              const int32_t* __restrict__ pcs, const T* __restrict__ x,
                                                              T* __restrict__ q, T dq) {
     constexpr int EPV = LdTraits<U>::EPV;
+    constexpr int BWD_RG = bwd_rows_per_warp<T, U>();
     __shared__ __align__(16) T xs[BWD_COLS];
     __shared__ T racc[BWD_ROWS];
     const int4 it = items[blockIdx.x];
@@ -1194,24 +1206,98 @@ __global__ void __launch_bounds__(BWD_THREADS) row_dot_kernel(const int4* __rest
         const int ncol = min(BWD_COLS, col1 - cbase);
         for (int i = threadIdx.x; i < BWD_COLS; i += BWD_THREADS) xs[i] = (i < ncol) ? x[cbase + i] : T(0);
         __syncthreads();
-        for (int r = row0 + warp; r < row1; r += BWD_THREADS / WARP) {
-            const int64_t o0 = prow[r];
-            const int nv = (int)((prow[r + 1] - o0) / EPV);
-            const int c0 = pcs[r];
-            const int v_lo = max(0, (cbase - c0) / EPV), v_hi = min(nv, (cbase + BWD_COLS - c0) / EPV);
-            if (v_lo >= v_hi) continue;                                   // warp-uniform
-            const uint4* src = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
-            const T* xr = xs + (c0 - cbase);
-            typename Pk<T>::acc_t acc2 = Pk<T>::zero();
+        if constexpr (BWD_RG == 1) {
+            for (int r = row0 + warp; r < row1; r += BWD_THREADS / WARP) {
+                const int64_t o0 = prow[r];
+                const int nv = (int)((prow[r + 1] - o0) / EPV);
+                const int c0 = pcs[r];
+                const int v_lo = max(0, (cbase - c0) / EPV), v_hi = min(nv, (cbase + BWD_COLS - c0) / EPV);
+                if (v_lo >= v_hi) continue;                                   // warp-uniform
+                const uint4* src = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
+                const T* xr = xs + (c0 - cbase);
+                typename Pk<T>::acc_t acc2 = Pk<T>::zero();
 #pragma unroll 4
-            for (int v = v_lo + lane; v < v_hi; v += WARP) {
-                const uint4 c = __ldg(src + v);
-                T xv[EPV];
-                load_state_vec(xr + (size_t)v * EPV, xv, EPV * (int)sizeof(T) / 16);
-                VecOps<T, U>::dot(c, xv, acc2);
+                for (int v = v_lo + lane; v < v_hi; v += WARP) {
+                    const uint4 c = __ldg(src + v);
+                    T xv[EPV];
+                    load_state_vec(xr + (size_t)v * EPV, xv, EPV * (int)sizeof(T) / 16);
+                    VecOps<T, U>::dot(c, xv, acc2);
+                }
+                const T acc = warp_sum(Pk<T>::sum(acc2));
+                if (lane == 0) racc[r - row0] += acc;
             }
-            const T acc = warp_sum(Pk<T>::sum(acc2));
-            if (lane == 0) racc[r - row0] += acc;
+            continue;
+        }
+        // A warp takes BWD_RG consecutive rows at a time and walks the LD vectors of the column chunk ("block vectors":
+        // 16-byte groups of columns counted from cbase -- every row layout of ld.cu starts at a multiple of EPV columns
+        // from the unit start): the x values of a block vector are read from shared memory ONCE and used for all the
+        // rows of the group (int8 LD: 64 bytes of x per 16 bytes of LD made the row-at-a-time form shared-memory
+        // bound, 1.7 TB/s), and the group's loads are independent requests in flight.
+        for (int r = row0 + BWD_RG * warp; r < row1; r += BWD_RG * (BWD_THREADS / WARP)) {
+            const uint4* src[BWD_RG];
+            int blo[BWD_RG], bhi[BWD_RG];
+            int lo = BWD_COLS / EPV, hi = 0;
+            bool aligned = true;
+#pragma unroll
+            for (int i = 0; i < BWD_RG; ++i) {
+                blo[i] = 0; bhi[i] = 0; src[i] = nullptr;
+                if (r + i < row1) {
+                    const int64_t o0 = prow[r + i];
+                    const int nv = (int)((prow[r + i + 1] - o0) / EPV);
+                    const int d = pcs[r + i] - cbase;                     // first stored column relative to the chunk
+                    aligned &= (d % EPV) == 0;
+                    const int dv = d / EPV;                               // exact when aligned
+                    blo[i] = max(0, dv); bhi[i] = min(BWD_COLS / EPV, dv + nv);
+                    src[i] = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U)) - dv;   // indexed by block vector
+                    if (blo[i] < bhi[i]) { lo = min(lo, blo[i]); hi = max(hi, bhi[i]); }
+                }
+            }
+            if (lo >= hi) continue;                                       // warp-uniform
+            if (aligned) {
+                typename Pk<T>::acc_t acc2[BWD_RG];
+#pragma unroll
+                for (int i = 0; i < BWD_RG; ++i) acc2[i] = Pk<T>::zero();
+                for (int vb = lo + lane; vb < hi; vb += WARP) {
+                    uint4 c[BWD_RG];
+                    bool in[BWD_RG];
+#pragma unroll
+                    for (int i = 0; i < BWD_RG; ++i) {
+                        in[i] = vb >= blo[i] && vb < bhi[i];
+                        if (in[i]) c[i] = __ldg(src[i] + vb);
+                    }
+                    T xv[EPV];
+                    load_state_vec(xs + (size_t)vb * EPV, xv, EPV * (int)sizeof(T) / 16);
+#pragma unroll
+                    for (int i = 0; i < BWD_RG; ++i)
+                        if (in[i]) VecOps<T, U>::dot(c[i], xv, acc2[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < BWD_RG; ++i) {
+                    const T acc = warp_sum(Pk<T>::sum(acc2[i]));
+                    if (lane == 0 && r + i < row1) racc[r + i - row0] += acc;
+                }
+            } else {
+                // a layout whose rows do not start on the chunk's vector grid: one row at a time
+                for (int i = 0; i < BWD_RG && r + i < row1; ++i) {
+                    const int rr = r + i;
+                    const int64_t o0 = prow[rr];
+                    const int nv = (int)((prow[rr + 1] - o0) / EPV);
+                    const int c0 = pcs[rr];
+                    const int v_lo = max(0, (cbase - c0) / EPV), v_hi = min(nv, (cbase + BWD_COLS - c0) / EPV);
+                    if (v_lo >= v_hi) continue;
+                    const uint4* s1 = reinterpret_cast<const uint4*>(packed + o0 * (int64_t)sizeof(U));
+                    const T* xr = xs + (c0 - cbase);
+                    typename Pk<T>::acc_t a2 = Pk<T>::zero();
+                    for (int v = v_lo + lane; v < v_hi; v += WARP) {
+                        const uint4 c = __ldg(s1 + v);
+                        T xv[EPV];
+                        load_state_vec(xr + (size_t)v * EPV, xv, EPV * (int)sizeof(T) / 16);
+                        VecOps<T, U>::dot(c, xv, a2);
+                    }
+                    const T acc = warp_sum(Pk<T>::sum(a2));
+                    if (lane == 0) racc[rr - row0] += acc;
+                }
+            }
         }
     }
     __syncthreads();

@@ -28,9 +28,28 @@ constexpr int FAST_WARPS = 10;
 #ifndef VB_CHAIN_WARP
 #define VB_CHAIN_WARP 8         // 8: the chain shares its sub-partition with A0 / C0 (the lightest bulk warps), 9: with A1 / C1 (measured: C2 1.006 vs 1.020 ms, C4 1.702 vs 1.734 ms)
 #endif
-constexpr int FAST_CHAIN_WARP = VB_CHAIN_WARP, FAST_PRODUCER_WARP = 17 - VB_CHAIN_WARP;
-__device__ __forceinline__ int fast_a_index(int warp) { return warp < 4 ? warp : -1; }
-__device__ __forceinline__ int fast_c_index(int warp) { return (warp >= 4 && warp < 8) ? warp - 4 : -1; }
+#ifndef VB_PRODUCER_WARP
+#define VB_PRODUCER_WARP (17 - VB_CHAIN_WARP)
+#endif
+#ifndef VB_A_BASE
+#define VB_A_BASE 0             // first of the four A warps
+#endif
+#ifndef VB_C_BASE
+#define VB_C_BASE 4             // first of the four C warps
+#endif
+constexpr int FAST_CHAIN_WARP = VB_CHAIN_WARP, FAST_PRODUCER_WARP = VB_PRODUCER_WARP;
+// Which share of the tiles (index 0..3, fast_tile) a bulk warp owns.  Index 3 owns the last tile of the block and is
+// the only live one over the last eighth of the rows, index 2 joins it over the last quarter, ...  Warp w runs on SM
+// sub-partition w % 4, so with index = warp for both roles the late, short rows of BOTH co-resident CTAs are served by
+// the four warps of ONE sub-partition while the other three idle.  smsp_rot = 2 places the four roles (A, C of the
+// CTA, A, C of its SM neighbour -- CTA b and CTA b + n_sm, by launch order) as a Latin square: every sub-partition
+// hosts the indices 0, 1, 2, 3 once.  smsp_rot = 1: only the C warps are shifted by one; 0: index = warp.
+__device__ __forceinline__ int fast_a_index(int warp, int rot) {
+    return (unsigned)(warp - VB_A_BASE) < 4u ? ((warp - VB_A_BASE + rot) & 3) : -1;
+}
+__device__ __forceinline__ int fast_c_index(int warp, int rot) {
+    return (unsigned)(warp - VB_C_BASE) < 4u ? ((warp - VB_C_BASE + rot) & 3) : -1;
+}
 constexpr int FAST_MAX_BLOCK = 4096;      // 128 threads x 32 columns
 constexpr int FR = 128;                   // published-f ring (columns)
 constexpr int HP = 258;                   // entries of the fixed-point prefix sum (>= 4096/16 + 1; HP * 8 a multiple of 16)
@@ -135,7 +154,10 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
     const uint32_t zaddr_code = sbase + FL.zero + 16;    // code 0: contributes nothing to a decoded dot / axpy
 
     const int tid = threadIdx.x, warp = tid / WARP, lane = tid % WARP;
-    const int ai = fast_a_index(warp), ci = fast_c_index(warp);
+    const bool second = (int)blockIdx.x >= p.n_sm;
+    const int rot_a = (p.smsp_rot == 2 && second) ? 2 : 0;
+    const int rot_c = p.smsp_rot == 0 ? 0 : rot_a + 1;
+    const int ai = fast_a_index(warp, rot_a), ci = fast_c_index(warp, rot_c);
     const int blk = p.blk_order[blockIdx.x];
     const int r0 = p.blk_row[blk], r1 = p.blk_row[blk + 1];
     const int B = r1 - r0;
@@ -308,6 +330,10 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                     const int nv = min(4, P - rg);
                     int mx[4];
                     [[maybe_unused]] int my[4], mz[4];
+#ifdef VB_TRACE2
+                    const bool tr2 = (wa == 3 && rg == 4);
+                    if (tr2) trace_ev(p, lane, 10, 0, u);
+#endif
                     if (anyb) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
@@ -323,6 +349,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
 #pragma unroll
                         for (int r = 0; r < 4; ++r) { my[r] = 0; mz[r] = 0; }
                     }
+#ifdef VB_TRACE2
+                    if (tr2) { asm volatile("" ::"r"(mx[0]), "r"(mx[3])); trace_ev(p, lane, 10, 1, u); }
+#endif
                     [[maybe_unused]] int acc[4][DP4A ? NLIMB : 1];
                     [[maybe_unused]] typename Pk<T>::acc_t acc2[4];
 #pragma unroll
@@ -352,6 +381,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                         uint4 cv[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
+#ifdef VB_TRACE2
+                        if (tr2 && c == NVT - 1) { trace_ev(p, lane, 10, 2, u); asm volatile("" ::"r"(cv[0].x), "r"(cv[3].w)); trace_ev(p, lane, 10, 3, u); }
+#endif
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             if constexpr (DP4A) {
@@ -370,6 +402,11 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                         }
                     }
                     if (rg == 0) trace_ev(p, lane, wa, 4, u);
+#ifdef VB_TRACE2
+                    if constexpr (DP4A) {
+                        if (tr2) { asm volatile("" ::"r"(acc[0][0]), "r"(acc[3][NLIMB - 1]), "r"(acc[1][1]), "r"(acc[2][0])); trace_ev(p, lane, 10, 4, u); }
+                    }
+#endif
                     if constexpr (DP4A) {
                         // exact integer totals: one REDUX per (row, digit); lane (rg + r) keeps the digits of row rg + r
 #pragma unroll
@@ -388,6 +425,11 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                         if ((lane & 7) == 0 && rr < nv) sm.partial[wa * RR + ((jl0 + rg + rr) & (RR - 1))] = acc1[0];
                     }
                     if (rg == 0) trace_ev(p, lane, wa, 5, u);
+#ifdef VB_TRACE2
+                    if constexpr (DP4A) {
+                        if (tr2) { asm volatile("" ::"r"(dig[0]), "r"(dig[NLIMB - 1])); trace_ev(p, lane, 10, 5, u); }
+                    }
+#endif
                 }
             }
             trace_ev(p, lane, wa, 6, u);
