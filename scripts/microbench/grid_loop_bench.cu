@@ -41,6 +41,17 @@ __device__ __forceinline__ void decode4_i2f(uint32_t w, float* o) {
         : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(w));
 }
 
+// two's-complement codes (a signed copy of the dense block, no bias): PRMT with sign replication (selector msb) extends a
+// byte to 32 bits, I2FP.F32.S32 converts it -- two ALU-side instructions per code and nothing on the FMA pipe
+__device__ __forceinline__ void decode4_i2fp(uint32_t w, float* o) {
+    int i0, i1, i2, i3;
+    asm("prmt.b32 %0, %1, 0, 0x8880;" : "=r"(i0) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0x9991;" : "=r"(i1) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0xaaa2;" : "=r"(i2) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0xbbb3;" : "=r"(i3) : "r"(w));
+    o[0] = __int2float_rn(i0); o[1] = __int2float_rn(i1); o[2] = __int2float_rn(i2); o[3] = __int2float_rn(i3);
+}
+
 constexpr int ROWS = 16, ROWB = 4096;
 
 // MODE 0: FFMA2 only (values fixed in registers)   1: + deltas from shared memory every row
@@ -88,6 +99,14 @@ __global__ void __launch_bounds__(MAXT, 1) k(int nrows, float* out, long long* c
             if (MODE == 5) {
                 const uint4 cv = lds128(rowp + rr * ROWB);
                 decode4_i2f(cv.x, v); decode4(cv.y, v + 4); decode4_i2f(cv.z, v + 8); decode4(cv.w, v + 12);
+            }
+            if (MODE == 7) {
+                const uint4 cv = lds128(rowp + rr * ROWB);
+                decode4_i2fp(cv.x, v); decode4_i2fp(cv.y, v + 4); decode4_i2fp(cv.z, v + 8); decode4_i2fp(cv.w, v + 12);
+            }
+            if (MODE == 8) {
+                const uint4 cv = lds128(rowp + rr * ROWB);
+                decode4_i2fp(cv.x, v); decode4(cv.y, v + 4); decode4_i2fp(cv.z, v + 8); decode4(cv.w, v + 12);
             }
             if (MODE == 6) {
                 const uint4 cv = lds128(rowp + rr * ROWB);
@@ -173,5 +192,7 @@ int main() {
     run<4>("4 plain, decode = 16 I2F.S8", out, cyc);
     run<5>("5 plain, decode = 8 I2F.S8 + 8 PRMT/4 FADD2", out, cyc);
     run<6>("6 plain, decode = 4 I2F.S8 + 12 PRMT/6 FADD2", out, cyc);
+    run<7>("7 plain, decode = 16 PRMT.sext + 16 I2FP", out, cyc);
+    run<8>("8 plain, 8 PRMT.sext/I2FP + 8 PRMT/4 FADD2", out, cyc);
     return 0;
 }

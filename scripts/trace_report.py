@@ -65,9 +65,10 @@ for w in CW:
           "  publish " + " | ".join(f"{perwarp(w, 6, 5, a, b):6.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))
 print("chain period/panel        " + "".join(f"{(CD[q[i + 1] - 1] - CD[q[i]]) / (q[i + 1] - 1 - q[i]):10.0f}" for i in range(4)))
 # fine-grained A row-group trace (builds with -DVB_TRACE2): A warp index 3, second row group of every panel
-T = [series(10, e) for e in range(6)]
+T = [series(10, e) for e in range(8)]
 if T[0]:
-    names = ["row-group top -> row bases loaded", "-> last tile's LDS.128 issued", "-> its data landed", "-> IDP.4A done", "-> REDUX + selects done"]
+    steps = [("row-group top -> row bases loaded", 0, 1), ("-> top of the last tile's iteration", 1, 6), ("-> its addresses computed", 6, 7),
+             ("-> its LDS.128 issued", 7, 2), ("-> its data landed", 2, 3), ("-> IDP.4A done", 3, 4), ("-> REDUX + selects done", 4, 5)]
     print("A (index 3) second row group, by block half (cycles):")
-    for i, nm in enumerate(names):
-        print(f"  {nm:36s}" + " | ".join(f"{avg(T[i], T[i + 1], a, b):7.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))
+    for nm, a_, b_ in steps:
+        print(f"  {nm:38s}" + " | ".join(f"{avg(T[a_], T[b_], a, b):7.0f}" for a, b in ((q[0], q[2]), (q[2], q[4]))))

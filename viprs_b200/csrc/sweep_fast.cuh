@@ -275,8 +275,14 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
         // (every row stores all of it: address = row base + own offset, no predicates) or boundary (the general,
         // branch-free form: a (row, vector) pair outside the row's range reads a 16-byte zero vector).
         const int wa = ai;
-        const uint32_t zaddr = DP4A ? zaddr_raw : zaddr_code;
-        const uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2;
+        uint32_t zaddr = DP4A ? zaddr_raw : zaddr_code;
+        uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2, a_rowmeta = sbase + FL.rowmeta;
+#ifdef VB_PIN_BASES
+        // experiment: force the ring bases to stay in registers (ptxas otherwise rebuilds some of them in front of their
+        // uses: S2UR SR_CgaCtaId -> ULEA -> LDC layout field -> IADD3).  Measured: C2 sweep 1.005 ms pinned vs 0.985 ms
+        // left alone -- the registers are worth more to the scheduler than the rebuilt addresses cost.
+        asm volatile("" : "+r"(a_rowbase), "+r"(a_pm2), "+r"(a_rowmeta), "+r"(zaddr));
+#endif
         int vown[NVT];
         uint32_t vaddr[NVT];
 #pragma unroll
@@ -339,8 +345,8 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                         for (int r = 0; r < 4; ++r) {
                             mx[r] = 0; my[r] = 0; mz[r] = 0;
                             if (r < nv) {
-                                const int4 m = sm.rowmeta[(jl0 + rg + r) & (RR - 1)];
-                                mx[r] = m.x; my[r] = m.y; mz[r] = m.z;
+                                const uint4 m = lds128(a_rowmeta + (uint32_t)((jl0 + rg + r) & (RR - 1)) * 16u);
+                                mx[r] = (int)m.x; my[r] = (int)m.y; mz[r] = (int)m.z;
                             }
                         }
                     } else {
@@ -362,6 +368,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                     }
 #pragma unroll
                     for (int c = 0; c < NVT; ++c) {
+#ifdef VB_TRACE2
+                        if (tr2 && c == NVT - 1) trace_ev(p, lane, 10, 6, u);
+#endif
                         if (!live[c]) continue;
                         uint32_t ad[4];
                         if (inter[c]) {
@@ -378,6 +387,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                             }
                             if (!__any_sync(0xffffffffu, any)) continue;     // no lane of the warp owns a live vector here
                         }
+#ifdef VB_TRACE2
+                        if (tr2 && c == NVT - 1) { asm volatile("" ::"r"(ad[0]), "r"(ad[3])); trace_ev(p, lane, 10, 7, u); }
+#endif
                         uint4 cv[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) cv[r] = lds128(ad[r]);
@@ -456,7 +468,11 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
     } else {
         // =============================== C: forward axpy ======================================
         const int wc = ci;
-        const uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2, a_alpha = sbase + FL.alpha;
+        uint32_t a_rowbase = sbase + FL.rowbase, a_pm2 = sbase + FL.panelmeta2, a_alpha = sbase + FL.alpha,
+                 a_rowmeta = sbase + FL.rowmeta, zc = zaddr_code;
+#ifdef VB_PIN_BASES
+        asm volatile("" : "+r"(a_rowbase), "+r"(a_pm2), "+r"(a_alpha), "+r"(a_rowmeta), "+r"(zc));
+#endif
         int vown[NVT];
         uint32_t vaddr[NVT];
 #pragma unroll
@@ -508,9 +524,9 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                             mx[r] = 0; my[r] = 0; mz[r] = 0; al[r] = T(0);
                             if (r < nv) {
                                 const int jl = jl0 + rg + r;
-                                const int4 m = sm.rowmeta[jl & (RR - 1)];
-                                mx[r] = m.x; my[r] = max(m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = m.z;
-                                al[r] = sm.alpha[jl & (RR - 1)];
+                                const uint4 m = lds128(a_rowmeta + (uint32_t)(jl & (RR - 1)) * 16u);
+                                mx[r] = (int)m.x; my[r] = max((int)m.y, (jl + WIN + EPV - 1) / EPV); mz[r] = (int)m.z;
+                                al[r] = lds_t(a_alpha + (uint32_t)(jl & (RR - 1)) * 4u, T());
                             }
                         }
                     } else {
@@ -537,7 +553,7 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                             for (int r = 0; r < 4; ++r) {
                                 const bool in = (vv >= my[r]) && (vv < mz[r]);
                                 any |= in;
-                                ad[r] = in ? vaddr[c] + (uint32_t)mx[r] : zaddr_code;
+                                ad[r] = in ? vaddr[c] + (uint32_t)mx[r] : zc;
                             }
                             if (!__any_sync(0xffffffffu, any)) continue;
                         }
