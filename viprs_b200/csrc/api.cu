@@ -33,7 +33,10 @@ struct DevBuf {            // scoped device allocation
 struct HostStreams {
     static constexpr int kMax = 8;
     cudaStream_t s[kMax] = {};
+    cudaStream_t out[kMax] = {};           // downloads of what is final before the update_q_factor pass
     cudaEvent_t join[kMax] = {};
+    cudaEvent_t swept[kMax] = {};
+    cudaEvent_t copied[kMax] = {};
     cudaEvent_t fork = nullptr;
     int n = 0;
 };
@@ -45,7 +48,10 @@ HostStreams* host_streams(int n) {
     if (!h.fork && cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     for (; h.n < n; ++h.n) {
         if (cudaStreamCreateWithFlags(&h.s[h.n], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&h.out[h.n], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&h.join[h.n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&h.swept[h.n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&h.copied[h.n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     return &h;
 }
@@ -118,24 +124,31 @@ int state_roundtrip(const viprs_b200_ld_t* ld, int32_t K, int32_t float_dtype, c
                 if (timing) cudaEventRecord(tev[1 + 3 * c], sc);
                 const int chunk = ld->n_chunks > 0 ? c : -1;
                 rc = K > 0 ? vb::incr_mix_f32(ld, K, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_lnp,
-                                              (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc)
+                                              (F*)d_ul, (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc, hs->swept[c])
                            : vb::incr_slab_f32(ld, (F*)d_beta, (F*)d_g, (F*)d_mu, (F*)d_eta, (F*)d_q, (F*)d_diff, (F*)d_ul,
-                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc);
+                                               (F*)d_sv, (F*)d_mm, (F)dq_scale, chunk, sc, hs->swept[c]);
                 if (rc == VIPRS_B200_EUNSUPPORTED && c == 0) { unsupported = true; rc = 0; break; }
                 if (timing) cudaEventRecord(tev[2 + 3 * c], sc);
-                auto downc = [&](void* dst, unsigned char* src, size_t off, size_t n) {
+                // everything but q is final once the sweep is done: it goes back on a second stream while the
+                // update_q_factor pass runs; q follows the pass
+                cudaStream_t so = hs->out[c];
+                auto downc = [&](void* dst, unsigned char* src, size_t off, size_t n, cudaStream_t s_) {
                     if (e == cudaSuccess && rc == 0 && n)
-                        e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(dst) + off, src + off, n, cudaMemcpyDeviceToHost, sc);
+                        e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(dst) + off, src + off, n, cudaMemcpyDeviceToHost, s_);
                 };
-                downc(var_gamma, d_g, ok_, bk); downc(var_mu, d_mu, ok_, bk); downc(eta, d_eta, o1, b1); downc(q, d_q, o1, b1);
-                downc(eta_diff, d_diff, o1, b1);
+                if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(so, hs->swept[c], 0);
+                downc(var_gamma, d_g, ok_, bk, so); downc(var_mu, d_mu, ok_, bk, so); downc(eta, d_eta, o1, b1, so);
+                downc(eta_diff, d_diff, o1, b1, so);
+                if (e == cudaSuccess && rc == 0) e = cudaEventRecord(hs->copied[c], so);
+                downc(q, d_q, o1, b1, sc);
+                if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(sc, hs->copied[c], 0);
                 if (timing) cudaEventRecord(tev[3 + 3 * c], sc);
                 if (e == cudaSuccess) e = cudaEventRecord(hs->join[c], sc);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hs->join[c], 0);
             }
             if (!unsupported) {
                 cudaError_t e2 = cudaStreamSynchronize(st);
-                for (int c = 0; c < nch; ++c) cudaStreamSynchronize(hs->s[c]);
+                for (int c = 0; c < nch; ++c) { cudaStreamSynchronize(hs->s[c]); cudaStreamSynchronize(hs->out[c]); }
                 if (timing) {
                     for (int c = 0; c < nch; ++c) {
                         float a = 0, b = 0, d2 = 0;

@@ -306,7 +306,7 @@ static int e_step_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_ga
 // two reads of the LD per call like the reference.  `chunk` >= 0 restricts the call to one row chunk of the handle.
 template <typename U, typename Model>
 static int launch_incremental(const viprs_b200_ld* ld, const typename Model::Args& ma, StateArgs<float> sa, float dq, int chunk,
-                              cudaStream_t st) {
+                              cudaStream_t st, cudaEvent_t swept = nullptr) {
     using T = float;
     if constexpr (Model::kHeavy || sizeof(U) == 8) {
         return VIPRS_B200_EUNSUPPORTED;
@@ -323,6 +323,10 @@ static int launch_incremental(const viprs_b200_ld* ld, const typename Model::Arg
         int rc;
         if (std::is_same<U, int8_t>::value) rc = launch_fast_ver<U, Model, 3, 1, true>(ld, p, ma, sa, st);
         else rc = launch_fast_ver<U, Model, 4, 1, true>(ld, p, ma, sa, st);
+        if (rc == 0 && swept != nullptr) {
+            const cudaError_t e = cudaEventRecord(swept, st);
+            if (e != cudaSuccess) return (int)e;
+        }
         if (rc == 0)
             rc = launch_row_dots<T, U>(ld->d_items_bwd + sub.item0, sub.item1 - sub.item0, ld->d_packed, ld->d_prow, ld->d_pcs,
                                        sa.eta_diff, sa.q, dq, st);
@@ -333,7 +337,7 @@ static int launch_incremental(const viprs_b200_ld* ld, const typename Model::Arg
 template <typename T>
 static int e_step_incremental_dispatch(const viprs_b200_ld* ld, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
                                        T* eta_diff, const T* u_logs, const T* shvt, const T* mu_mult, T dq, int chunk,
-                                       cudaStream_t st) {
+                                       cudaStream_t st, cudaEvent_t swept = nullptr) {
     if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !u_logs || !shvt || !mu_mult)
         return VIPRS_B200_EINVAL;
     if constexpr (sizeof(T) != 4) {
@@ -341,14 +345,14 @@ static int e_step_incremental_dispatch(const viprs_b200_ld* ld, const T* std_bet
     } else {
         typename SlabModel<T>::Args ma{std_beta, u_logs, shvt, mu_mult, var_gamma, var_mu, dq};
         StateArgs<T> sa{eta, q, eta_diff};
-        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), SlabModel<T>>(ld, ma, sa, dq, chunk, st); });
+        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), SlabModel<T>>(ld, ma, sa, dq, chunk, st, swept); });
     }
 }
 
 template <typename T>
 static int mixture_incremental_dispatch(const viprs_b200_ld* ld, int K, const T* std_beta, T* var_gamma, T* var_mu, T* eta, T* q,
                                         T* eta_diff, const T* log_null_pi, const T* u_logs, const T* shvt, const T* mu_mult,
-                                        T dq, int chunk, cudaStream_t st) {
+                                        T dq, int chunk, cudaStream_t st, cudaEvent_t swept = nullptr) {
     if (!ld || !std_beta || !var_gamma || !var_mu || !eta || !q || !eta_diff || !log_null_pi || !u_logs || !shvt || !mu_mult)
         return VIPRS_B200_EINVAL;
     if constexpr (sizeof(T) != 4) {
@@ -357,7 +361,7 @@ static int mixture_incremental_dispatch(const viprs_b200_ld* ld, int K, const T*
         if (K < 1 || K > 4) return VIPRS_B200_EUNSUPPORTED;
         typename MixModel<T, 4>::Args ma{std_beta, u_logs, shvt, mu_mult, log_null_pi, var_gamma, var_mu, dq, K};
         StateArgs<T> sa{eta, q, eta_diff};
-        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), MixModel<T, 4>>(ld, ma, sa, dq, chunk, st); });
+        return for_ld_dtype<T>(ld, [&](auto tag) { return launch_incremental<decltype(tag), MixModel<T, 4>>(ld, ma, sa, dq, chunk, st, swept); });
     }
 }
 

@@ -93,11 +93,12 @@ RingGeometry fast_ring_geometry(const viprs_b200_ld* ld);
 // build the dense symmetric block layout if it does not exist yet; 0 or an error code
 int ensure_dense(const viprs_b200_ld* ld, cudaStream_t stream);
 // incremental-q sweeps of one row chunk (chunk < 0: everything), see launch.cuh launch_incremental; defined in
-// slab_f32.cu / mix_f32.cu, used by the host-state drop-ins in api.cu
+// slab_f32.cu / mix_f32.cu, used by the host-state drop-ins in api.cu.  `swept` (nullable) is recorded on `st` between
+// the sweep and the update_q_factor pass: everything but q is final from there on.
 int incr_slab_f32(const viprs_b200_ld* ld, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
                   float* eta_diff, const float* u_logs, const float* shvt, const float* mu_mult, float dq, int chunk,
-                  cudaStream_t st);
+                  cudaStream_t st, cudaEvent_t swept = nullptr);
 int incr_mix_f32(const viprs_b200_ld* ld, int K, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
                  float* eta_diff, const float* log_null_pi, const float* u_logs, const float* shvt, const float* mu_mult,
-                 float dq, int chunk, cudaStream_t st);
+                 float dq, int chunk, cudaStream_t st, cudaEvent_t swept = nullptr);
 }  // namespace vb

@@ -12,9 +12,9 @@ extern "C" int viprs_b200_e_step_mixture_f32(const viprs_b200_ld_t* ld, int32_t 
 
 int vb::incr_mix_f32(const viprs_b200_ld* ld, int K, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
                      float* eta_diff, const float* log_null_pi, const float* u_logs, const float* shvt, const float* mu_mult,
-                     float dq, int chunk, cudaStream_t st) {
+                     float dq, int chunk, cudaStream_t st, cudaEvent_t swept) {
     return vb::mixture_incremental_dispatch<float>(ld, K, std_beta, var_gamma, var_mu, eta, q, eta_diff, log_null_pi, u_logs,
-                                                   shvt, mu_mult, dq, chunk, st);
+                                                   shvt, mu_mult, dq, chunk, st, swept);
 }
 
 extern "C" int viprs_b200_e_step_mixture_incremental_f32(const viprs_b200_ld_t* ld, int32_t K, const float* std_beta,

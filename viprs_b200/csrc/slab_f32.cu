@@ -30,9 +30,9 @@ extern "C" int viprs_b200_e_step_fused_f32(const viprs_b200_ld_t* ld, const floa
 
 int vb::incr_slab_f32(const viprs_b200_ld* ld, const float* std_beta, float* var_gamma, float* var_mu, float* eta, float* q,
                       float* eta_diff, const float* u_logs, const float* shvt, const float* mu_mult, float dq, int chunk,
-                      cudaStream_t st) {
+                      cudaStream_t st, cudaEvent_t swept) {
     return vb::e_step_incremental_dispatch<float>(ld, std_beta, var_gamma, var_mu, eta, q, eta_diff, u_logs, shvt, mu_mult, dq,
-                                                  chunk, st);
+                                                  chunk, st, swept);
 }
 
 extern "C" int viprs_b200_e_step_incremental_f32(const viprs_b200_ld_t* ld, const float* std_beta, float* var_gamma,

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                     live[c] = (tb + 32 > vmin) && (tb < vmax);
                     inter[c] = quad && (tb >= lo_all) && (tb + 32 <= hi_all);
                 } else {
-#ifdef VB_LIVE_ALL
+#ifndef VB_NO_LIVE_ALL
                     live[c] = (tb + 32 > vmin) && (tb < vmax); inter[c] = false;     // dead tiles skipped, general form otherwise
 #else
                     live[c] = true; inter[c] = false;        // general form only (see CLASSIFY)
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                     live[c] = (tb + 32 > max(vmin, cut0)) && (tb < vmax);
                     inter[c] = quad && (tb >= lo_c) && (tb + 32 <= hi_c);
                 } else {
-#ifdef VB_LIVE_ALL
+#ifndef VB_NO_LIVE_ALL
                     live[c] = (tb + 32 > max(vmin, cut0)) && (tb < vmax); inter[c] = false;
 #else
                     live[c] = true; inter[c] = false;
