@@ -340,6 +340,14 @@ __global__ void __launch_bounds__(fast_threads<VER>(), 2) sweep_fast_kernel(cons
                     const int nv = min(4, P - rg);
                     int mx[4];
                     [[maybe_unused]] int my[4], mz[4];
+#ifdef VB_WHATIF_PAD
+                    // timing experiment: VB_WHATIF_PAD never-executed instructions in the middle of the row-group loop
+                    // (how sensitive is the sweep to the size of a role's loop body?)
+                    if (p.n_blocks < 0) {
+#pragma unroll
+                        for (int z = 0; z < VB_WHATIF_PAD; ++z) asm volatile("nanosleep.u32 1;");
+                    }
+#endif
 #ifdef VB_TRACE2
                     const bool tr2 = (wa == 3 && rg == 4);
                     if (tr2) trace_ev(p, lane, 10, 0, u);
