@@ -67,11 +67,26 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
     double acc[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[s] = 0.0;
-    for (int j = row0 + chunk * blockDim.x + threadIdx.x; j < row1; j += chunks * blockDim.x) {
+    // the operands of the next row are requested before the arithmetic of the current one (the loop is otherwise a chain of
+    // load -> ~280 instructions -> load: 9 warps per issue slot waiting on memory at G = 256)
+    struct Row { T g, mu, et, qv, df, sb; double n; };
+    auto fetch = [&](int j, Row& r) {
         const size_t e = layout == 0 ? (size_t)c * M + j : (size_t)j * ncol + c;
-        const double g = (double)var_gamma[e];
-        const double mu = (double)var_mu[e];
-        const double n = n_per_snp[j];
+        r.g = var_gamma[e]; r.mu = var_mu[e]; r.n = n_per_snp[j];
+        if (per_snp) {
+            const size_t ev = layout == 0 ? e : (size_t)j;
+            r.et = eta[ev]; r.qv = q[ev]; r.df = eta_diff[ev]; r.sb = std_beta[j];
+        }
+    };
+    const int jstep = chunks * blockDim.x;
+    int j = row0 + chunk * blockDim.x + threadIdx.x;
+    Row cur{}, nxt{};
+    if (j < row1) fetch(j, cur);
+    for (; j < row1; j += jstep, cur = nxt) {
+        if (j + jstep < row1) fetch(j + jstep, nxt);
+        const double g = (double)cur.g;
+        const double mu = (double)cur.mu;
+        const double n = cur.n;
         const double vt = n * nscale + th.tau_beta;
         const double gc = clip_res(g);
         acc[VIPRS_B200_S_GAMMA] += g;                                               // VIPRS.py:434
@@ -83,8 +98,7 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
         acc[VIPRS_B200_S_G_LOG_TAU] += gc * log_tau<T>(same_tau ? vt : n * nscale_l + tl.tau_beta);   // VIPRS.py:565 (log_var_tau cache)
         acc[VIPRS_B200_S_GC_ZETA] += gc * (mu * mu + ivt);                          // VIPRS.py:571-573
         if (per_snp) {
-            const size_t ev = layout == 0 ? e : (size_t)j;
-            const double et = (double)eta[ev];
+            const double et = (double)cur.et;
             double pip;
             if (layout == 0) {
                 pip = g;
@@ -94,12 +108,12 @@ __global__ void __launch_bounds__(EM_THREADS) sums_kernel(int M, int ncol, int l
                 pip = (double)s;
             }
             const double ng = clip_res(1.0 - pip);
-            acc[VIPRS_B200_S_ETA_Q] += q_scale * et * (double)q[ev];                // VIPRS.py:455
-            acc[VIPRS_B200_S_BETA_ETA] += (double)std_beta[j] * et;                 // VIPRS.py:469
+            acc[VIPRS_B200_S_ETA_Q] += q_scale * et * (double)cur.qv;               // VIPRS.py:455
+            acc[VIPRS_B200_S_BETA_ETA] += (double)cur.sb * et;                      // VIPRS.py:469
             acc[VIPRS_B200_S_NG_LOGNG] += ng * log_one_minus<T>(pip, ng);                             // VIPRS.py:563
             acc[VIPRS_B200_S_NGCLIP] += ng;
             acc[VIPRS_B200_S_ETA2] += et * et;                                      // VIPRS.py:703
-            acc[VIPRS_B200_S_MAX_DIFF] = fmax(acc[VIPRS_B200_S_MAX_DIFF], fabs((double)eta_diff[ev]));   // VIPRS.py:997
+            acc[VIPRS_B200_S_MAX_DIFF] = fmax(acc[VIPRS_B200_S_MAX_DIFF], fabs((double)cur.df));   // VIPRS.py:997
         }
     }
     // block reduction in a fixed order: lanes by xor-shuffle, then warps 0..7 sequentially
