@@ -57,6 +57,23 @@ def test_cpp_e_step_host_dropin_matches_oracle(vb, oracle_built, tn, un, n_sweep
         assert relmax(got[k], ref[k]) <= TOL[T], (k, relmax(got[k], ref[k]))
 
 
+@pytest.mark.parametrize("rot", ["0", "1", "2"])
+@pytest.mark.parametrize("un", ["i8", "i16"])
+def test_bulk_warp_placement_modes_match_oracle(vb, oracle_built, monkeypatch, rot, un):
+    """VIPRS_B200_SMSP_ROT (sweep_fast.cuh: which SM sub-partition hosts which share of the tiles; read at every launch):
+    every placement is the same arithmetic -- blocks wide enough for all eight tiles, more blocks than SMs so that the
+    second-CTA-of-an-SM rotation of mode 2 is exercised too."""
+    monkeypatch.setenv("VIPRS_B200_SMSP_ROT", rot)
+    T = np.float32
+    rng = np.random.default_rng(300 + int(rot))
+    P = make_block_ld(rng, (4096, 2100) + (40,) * 170, LD_DT[un], T)
+    hy = _hyper(rng, P, T)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, 2)
+    got = _sweeps(vb.cpp_e_step, P, T, hy, 2)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(got[k], ref[k]) <= TOL[T], (k, relmax(got[k], ref[k]))
+
+
 @pytest.mark.parametrize("tn,un", [("f32", "i8"), ("f64", "f64")])
 def test_symmetric_layout_matches_oracle(vb, oracle_built, tn, un):
     """`low_memory=False` (symmetric rows incl. the unit diagonal, e_step.hpp:423-428)."""
