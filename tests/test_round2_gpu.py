@@ -227,6 +227,22 @@ def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
             # the incremental-q route (the reference's own q bookkeeping; what the host-state round trip and `e2e` run)
             ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
             res["incr"] = _sweeps(lambda lb, ip, dat, *a: vb.cpp_e_step_resident(ld, *a[:-3], a[-3], False), P, T, hy, n_sweeps)
+
+            # the ONE-PASS sweep (what fit() runs every iteration and bench.py times: IDP.4A backward dots on a block-scaled
+            # fixed-point eta_old) through the device entry, with 3 (21-bit) and 4 (28-bit) digits: the host drop-ins above
+            # take the incremental route for float32, which has no backward dots at all
+            def onepass(lb, ip, dat, beta, g, mu, eta, q, diff, ul_, sv_, mm_, dq, *rest):
+                dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (beta, g, mu, eta, q, diff, ul_, sv_, mm_)]
+                vb.e_step_device(ld, *dev, dq, True)
+                torch.cuda.synchronize()
+                for host, d_ in zip((g, mu, eta, q, diff), (dev[1], dev[2], dev[3], dev[4], dev[5])):
+                    host[...] = d_.cpu().numpy()
+            res["one3"] = _sweeps(onepass, P, T, hy, n_sweeps)
+            os.environ["VIPRS_B200_LIMBS"] = "4"
+            try:
+                res["one4"] = _sweeps(onepass, P, T, hy, n_sweeps)
+            finally:
+                del os.environ["VIPRS_B200_LIMBS"]
             ld.destroy()
     rec = {}
     for k in ("eta", "var_gamma", "var_mu", "q"):
@@ -236,7 +252,11 @@ def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
                   "ours_limbs4_vs_ref64": relmax(res["got4"][k], res["ref_float64"][k]),
                   "limbs3_vs_limbs4": relmax(res["got3"][k], res["got4"][k]),
                   "incremental_vs_ref32": relmax(res["incr"][k], res["ref_float32"][k]),
-                  "incremental_vs_ref64": relmax(res["incr"][k], res["ref_float64"][k])}
+                  "incremental_vs_ref64": relmax(res["incr"][k], res["ref_float64"][k]),
+                  "onepass_vs_ref32": relmax(res["one3"][k], res["ref_float32"][k]),
+                  "onepass_vs_ref64": relmax(res["one3"][k], res["ref_float64"][k]),
+                  "onepass_limbs4_vs_ref64": relmax(res["one4"][k], res["ref_float64"][k]),
+                  "onepass_limbs3_vs_limbs4": relmax(res["one3"][k], res["one4"][k])}
     _record(f"c2_block_int8_{n_sweeps}_sweeps", rec)
     print(json.dumps(rec))
     for k in ("eta", "var_gamma"):
@@ -247,6 +267,8 @@ def test_c2_block_baseline_params(vb, oracle_built, n_sweeps):
         # the 21-bit fixed-point representation adds nothing visible next to float32 rounding
         assert r["limbs3_vs_limbs4"] <= max(1e-4, 2 * r["floor_ref32_vs_ref64"]), (k, r)
         assert r["incremental_vs_ref32"] <= 1e-4 or r["incremental_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
+        assert r["onepass_vs_ref32"] <= 1e-4 or r["onepass_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
+        assert r["onepass_limbs3_vs_limbs4"] <= max(1e-4, 2 * r["floor_ref32_vs_ref64"]), (k, r)
 
 
 @pytest.mark.parametrize("n_sweeps", [10, 50])
@@ -272,16 +294,35 @@ def test_c4_block_baseline_params(vb, oracle_built, n_sweeps):
                    inp["std_beta"].numpy().astype(T), st["var_gamma"], st["var_mu"], st["eta"], st["q"], st["eta_diff"],
                    lnp, ul, sv, mm, inp["dq_scale"], 1, True)
             res[name + ("32" if T == np.float32 else "64")] = st
+        if T == np.float32:
+            # the one-pass mixture sweep (what VIPRSMix.fit runs every iteration) through the device entry: the float32 host
+            # drop-in above takes the incremental route
+            import torch
+            ld = vb.DeviceLD(inp["ld_data"].numpy(), inp["ld_indptr"].numpy(), inp["ld_left_bound"].numpy())
+            dev = {"beta": torch.from_numpy(inp["std_beta"].numpy().astype(T)).cuda(), "lnp": torch.from_numpy(lnp).cuda(),
+                   "ul": torch.from_numpy(ul).cuda(), "sv": torch.from_numpy(sv).cuda(), "mm": torch.from_numpy(mm).cuda(),
+                   "var_gamma": torch.from_numpy(C(np.tile(pis, (M, 1)))).cuda(), "var_mu": torch.zeros((M, K), dtype=torch.float32, device="cuda"),
+                   "eta": torch.zeros(M, dtype=torch.float32, device="cuda"), "q": torch.zeros(M, dtype=torch.float32, device="cuda"),
+                   "eta_diff": torch.zeros(M, dtype=torch.float32, device="cuda")}
+            for _ in range(n_sweeps):
+                vb.e_step_mixture_device(ld, dev["beta"], dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"],
+                                         dev["lnp"], dev["ul"], dev["sv"], dev["mm"], inp["dq_scale"], True)
+            torch.cuda.synchronize()
+            res["one32"] = {k: dev[k].cpu().numpy() for k in ("var_gamma", "var_mu", "eta", "q", "eta_diff")}
+            ld.destroy()
     rec = {}
     for k in ("eta", "var_gamma", "var_mu", "q"):
         rec[k] = {"floor_ref32_vs_ref64": relmax(res["ref32"][k], res["ref64"][k]),
                   "ours_vs_ref32": relmax(res["got32"][k], res["ref32"][k]),
-                  "ours_vs_ref64": relmax(res["got32"][k], res["ref64"][k])}
+                  "ours_vs_ref64": relmax(res["got32"][k], res["ref64"][k]),
+                  "onepass_vs_ref32": relmax(res["one32"][k], res["ref32"][k]),
+                  "onepass_vs_ref64": relmax(res["one32"][k], res["ref64"][k])}
     _record(f"c4_block_int16_K4_{n_sweeps}_sweeps", rec)
     print(json.dumps(rec))
     for k in ("eta", "var_gamma"):
         r = rec[k]
         assert r["ours_vs_ref32"] <= 1e-4 or r["ours_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
+        assert r["onepass_vs_ref32"] <= 1e-4 or r["onepass_vs_ref64"] <= 2 * r["floor_ref32_vs_ref64"], (k, r)
 
 
 # ---------------------------------------------------------------------------------------------------------
