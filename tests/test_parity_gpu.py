@@ -218,6 +218,34 @@ def test_device_path_and_ld_info(vb, oracle_built):
     assert relmax(dev["q"].cpu().numpy(), P["dq"] * ((R + R.T) @ eta)) <= 1e-4
 
 
+@pytest.mark.parametrize("un", ["i8", "i16", "f32"])
+@pytest.mark.parametrize("n_sweeps", [1, 3])
+def test_one_pass_device_sweep_matches_oracle(vb, oracle_built, un, n_sweeps):
+    """The ONE-PASS float32 sweep (viprs_b200_e_step_f32 on device arrays: what fit() runs every iteration -- backward
+    dots ahead of the chain, forward axpys behind it) on ragged blocks, for every LD storage type.  The float32 host
+    drop-ins take the incremental route, so this entry needs its own edge cases: 1- and 2-SNP blocks, a block that
+    fills all eight tiles, blocks that end inside a tile."""
+    import torch
+    T = np.float32
+    rng = np.random.default_rng(400 + n_sweeps)
+    P = make_block_ld(rng, (257, 64, 1, 2, 33, 4096, 700, 17, 1500), LD_DT[un], T)
+    hy = _hyper(rng, P, T)
+    u_logs, shvt, mm, pi = hy
+    M = P["M"]
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    dev = {k: torch.zeros(M, dtype=torch.float32, device="cuda") for k in ("var_mu", "eta", "q", "eta_diff")}
+    dev["var_gamma"] = torch.full((M,), pi, dtype=torch.float32, device="cuda")
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    beta, ul, sv, mmd = c(P["beta"]), c(u_logs), c(shvt), c(mm)
+    for _ in range(n_sweeps):
+        vb.e_step_device(ld, beta, dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"], ul, sv, mmd,
+                         P["dq"], True)
+    ref = _sweeps(oracle_built.e_step, P, T, hy, n_sweeps)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(dev[k].cpu().numpy(), ref[k]) <= TOL[T], (k, relmax(dev[k].cpu().numpy(), ref[k]))
+    ld.destroy()
+
+
 def test_non_block_ld_is_tiled_not_refused(vb):
     """A single huge 'block' (banded genome-wide LD, no independent blocks at all) used to be refused; it is now swept
     in 1024-row tiles (parity: tests/test_round2_gpu.py::test_banded_ld_is_swept_in_order).  Only the grid sweep,
