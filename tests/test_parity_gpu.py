@@ -169,6 +169,32 @@ def test_cpp_e_step_mixture_matches_oracle(vb, oracle_built, tn, un, K):
         assert relmax(got[k], ref[k]) <= TOL[T], (k, relmax(got[k], ref[k]))
 
 
+@pytest.mark.parametrize("un,K", [("i16", 4), ("i8", 2), ("i16", 1), ("f32", 3)])
+def test_one_pass_device_mixture_sweep_matches_oracle(vb, oracle_built, un, K):
+    """The one-pass float32 mixture sweep (viprs_b200_e_step_mixture_f32 on device arrays, what VIPRSMix.fit runs) on ragged
+    blocks; the float32 host drop-in above takes the incremental route for K <= 4."""
+    import torch
+    T = np.float32
+    rng = np.random.default_rng(60 + K)
+    P = make_block_ld(rng, (300, 64, 1, 2, 45, 4096, 500, 1200), LD_DT[un], T)
+    hy = _mix_hyper(rng, P, T, K)
+    u_logs, shvt, mm, lnp, pis = hy
+    M = P["M"]
+    ref = _mix_sweeps(oracle_built.e_step_mixture, P, T, hy, K, 3)
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dev = {"var_gamma": c(np.tile(pis.astype(T), (M, 1))), "var_mu": torch.zeros((M, K), dtype=torch.float32, device="cuda")}
+    for k in ("eta", "q", "eta_diff"):
+        dev[k] = torch.zeros(M, dtype=torch.float32, device="cuda")
+    beta, ul, sv, mmd, lnpd = c(P["beta"]), c(u_logs), c(shvt), c(mm), c(lnp)
+    for _ in range(3):
+        vb.e_step_mixture_device(ld, beta, dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"], lnpd, ul, sv,
+                                 mmd, P["dq"], True)
+    for k in ("eta", "var_gamma", "var_mu", "q", "eta_diff"):
+        assert relmax(dev[k].cpu().numpy(), ref[k]) <= TOL[T], (k, relmax(dev[k].cpu().numpy(), ref[k]))
+    ld.destroy()
+
+
 def test_golden_raw_sweeps(vb):
     """Against the committed reference outputs (no oracle involved): cpp_e_step f64 / int16 LD."""
     d, ch = load_golden("cpp_e_step_f64_i16.npz")
