@@ -50,6 +50,26 @@ def _sweeps(fn, P, T, hy, n_sweeps, st=None):
     return st
 
 
+def _device_sweeps(vb, P, T, hy, n_sweeps):
+    """The ONE-PASS sweep through the device entry (viprs_b200_e_step_f32 / _f64): what fit() runs every iteration.  The
+    float32 host drop-ins (vb.cpp_e_step) take the incremental route, which only exists as kernel version 1."""
+    import torch
+    M = P["M"]
+    u_logs, shvt, mm, pi = hy
+    td = torch.float32 if T == np.float32 else torch.float64
+    dev = {k: torch.zeros(M, dtype=td, device="cuda") for k in ("var_mu", "eta", "q", "eta_diff")}
+    dev["var_gamma"] = torch.full((M,), pi, dtype=td, device="cuda")
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ld = vb.DeviceLD(P["data"], P["indptr"], P["lb"])
+    beta, ul, sv, mmd = c(P["beta"]), c(u_logs), c(shvt), c(mm)
+    for _ in range(n_sweeps):
+        vb.e_step_device(ld, beta, dev["var_gamma"], dev["var_mu"], dev["eta"], dev["q"], dev["eta_diff"], ul, sv, mmd, P["dq"], True)
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in dev.items()}
+    ld.destroy()
+    return out
+
+
 def _record(name, payload):
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
@@ -472,7 +492,7 @@ def test_kernel_version_2_matches_oracle(vb, oracle_built, tn, un, blocks, monke
     P = make_block_ld(rng, blocks, U, T)
     hy = _hyper(rng, P["M"], T)
     ref = _sweeps(oracle_built.e_step, P, T, hy, 3)
-    got = _sweeps(vb.cpp_e_step, P, T, hy, 3)
+    got = _device_sweeps(vb, P, T, hy, 3)            # the device entry: the host drop-in would run version 1 (incremental route)
     # e_step.hpp:410-413: an update with |eta_diff| < eps is skipped and var_mu / var_gamma keep their previous value; a
     # SNP whose |eta_diff| sits at eps (1.2e-7) is skipped by one float32 evaluation order and not by another, so these
     # two arrays are compared where BOTH sides performed the update (eta / q move by at most eps either way)
