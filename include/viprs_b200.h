@@ -222,7 +222,9 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
  * (var_gamma, var_mu, eta, q, eta_diff) comes back; returns after the stream has drained.  Pinned host buffers make the
  * copies asynchronous.  Where the incremental sweep applies (float32 state, LD blocks <= 4096 SNPs) the call runs
  * viprs_b200_e_step_*incremental_f32 in row chunks on internal streams, so that the copies of one chunk overlap the sweep
- * of another, and q_is_consistent is irrelevant.  Otherwise: q_is_consistent != 0: the caller vouches that
+ * of another (everything but q goes back to the host while the update_q_factor pass of its chunk still runs), and
+ * q_is_consistent is irrelevant.  VIPRS_B200_E2E_TIMING=1 in the environment prints the device timeline of a call, per
+ * chunk, to stderr.  Otherwise: q_is_consistent != 0: the caller vouches that
  * q = dq (R - I) eta on entry (true on every iteration of VIPRS.fit unless `param_0` was given) and the two extra LD
  * passes of viprs_b200_q_offset_* are skipped. */
 int viprs_b200_cpp_e_step_resident(const viprs_b200_ld_t* ld, int32_t float_dtype, const void* std_beta, void* var_gamma,
