@@ -220,7 +220,7 @@ int viprs_b200_cpp_e_step_mixture(int32_t M, int32_t K, const int32_t* ld_left_b
  * host memory, as the reference does: per call the arrays cpp_e_step reads go host->device (std_beta, var_gamma, var_mu,
  * eta, q, u_logs, sqrt_half_var_tau, mu_mult), one sweep runs, q is materialised, and what cpp_e_step writes
  * (var_gamma, var_mu, eta, q, eta_diff) comes back; returns after the stream has drained.  Pinned host buffers make the
- * copies asynchronous.  Where the incremental sweep applies (float32 state, LD blocks <= 4096 SNPs) the call runs
+ * copies asynchronous (and let the uploads of a chunk go out as one batched copy).  Where the incremental sweep applies (float32 state, LD blocks <= 4096 SNPs) the call runs
  * viprs_b200_e_step_*incremental_f32 in row chunks on internal streams, so that the copies of one chunk overlap the sweep
  * of another (everything but q goes back to the host while the update_q_factor pass of its chunk still runs), and
  * q_is_consistent is irrelevant.  VIPRS_B200_E2E_TIMING=1 in the environment prints the device timeline of a call, per
